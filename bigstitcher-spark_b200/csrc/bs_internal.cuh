@@ -1,0 +1,107 @@
+// Internal declarations shared by the translation units of libbsgpu.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "bsgpu.h"
+
+struct bs_volume {
+    void* dev = nullptr;
+    long long dims[3] = {0, 0, 0};
+    int dtype = 0;
+    bool owned = false;
+};
+
+struct bs_prof_entry {
+    double ms = 0.0;
+    long long launches = 0;
+};
+
+struct bs_pending_event {
+    cudaEvent_t a, b;
+    std::string tag;
+};
+
+// Workspace of the phase-correlation pipeline (grown on demand, reused between pairs).
+struct bs_pcm_workspace {
+    void* spec_a = nullptr;      // complex64 [Pz][Py][pitch]; also the real PCM (in place)
+    void* spec_b = nullptr;
+    size_t spec_bytes = 0;
+    void* crop[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // double-buffered device crops (host input)
+    size_t crop_bytes = 0;
+    void* tables = nullptr;      // PcmDeviceTables*: twiddles + blend-extension profiles per axis
+    void* small = nullptr;       // device scratch for peaks / pearson sums
+    size_t small_bytes = 0;
+    void* small_host = nullptr;  // pinned mirror
+    cudaEvent_t crop_ready[2] = {nullptr, nullptr};
+    cudaEvent_t crop_free[2] = {nullptr, nullptr};
+};
+
+struct bs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    std::unordered_map<unsigned long long, bs_volume> vols;
+    unsigned long long next_handle = 1;
+    long long launches = 0;
+    bool prof = false;
+    std::map<std::string, bs_prof_entry> prof_entries;
+    std::vector<bs_pending_event> prof_pending;
+    bs_pcm_workspace ws;
+    void* fuse_views_dev = nullptr;   // device copy of view descriptors
+    size_t fuse_views_cap = 0;
+    void* fuse_out = nullptr;         // device staging for host outputs
+    size_t fuse_out_cap = 0;
+    int sm_count = 148;
+    bool pcm_attr_done = false;       // cudaFuncSetAttribute(max dynamic smem) done on this device
+};
+
+int bs_set_error(bs_ctx* ctx, int code, const char* fmt, ...);
+
+#define BS_CUDA(ctx, call)                                                                   \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return bs_set_error((ctx), e__ == cudaErrorMemoryAllocation ? BS_ERR_NOMEM       \
+                                                                        : BS_ERR_CUDA,       \
+                                "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),     \
+                                __FILE__, __LINE__);                                         \
+    } while (0)
+
+// RAII-less profiling bracket around one kernel launch.
+struct bs_launch_scope {
+    bs_ctx* ctx;
+    cudaEvent_t a = nullptr, b = nullptr;
+    const char* tag;
+    bs_launch_scope(bs_ctx* c, const char* t) : ctx(c), tag(t) {
+        ctx->launches++;
+        if (ctx->prof) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, ctx->stream);
+        }
+    }
+    ~bs_launch_scope() {
+        if (a) {
+            cudaEventRecord(b, ctx->stream);
+            ctx->prof_pending.push_back({a, b, tag});
+        }
+    }
+};
+
+void bs_profile_drain(bs_ctx* ctx);
+
+// device-buffer helper: (re)allocate when too small
+int bs_ensure_dev(bs_ctx* ctx, void** p, size_t* cap, size_t need);
+
+// pcm.cu
+void bs_pcm_workspace_free(bs_ctx* ctx);

@@ -1,0 +1,218 @@
+// Content-based fusion weights (Preibisch et al.): c = G_s2 * (I - G_s1 * I)^2 on the source
+// volume, precomputed once per view and sampled by the fusion kernel (SURVEY.md A.2 step 3;
+// FusionType AVG_CONTENT / AVG_BLEND_CONTENT, J/SparkAffineFusion.java:124).
+//
+// Separable truncated Gaussian (half size max(2, int(3*sigma+0.5)+1), normalised), single-mirror
+// border.  Each pass stages whole lines in shared memory: x pass = LINES rows per CTA, y/z pass =
+// a [len][32] column block (x-fastest, so global accesses stay coalesced).
+#include <cmath>
+#include <vector>
+
+#include "bs_internal.cuh"
+
+#define GA_THREADS 256
+#define GA_SMEM_MAX 232448
+
+extern __shared__ __align__(16) float ga_sm[];
+
+__device__ __forceinline__ int mirror_single(int i, int n) {
+    if (n == 1) return 0;
+    const int period = 2 * n - 2;
+    i %= period;
+    if (i < 0) i += period;
+    return i < n ? i : period - i;
+}
+
+struct GaussArgs {
+    const float* in;
+    float* out;
+    int dims[3];
+    int axis;
+    const float* kern;  // 2*r+1 taps
+    int r;
+    int lines;          // x pass: rows per CTA
+};
+
+// x pass: ga_sm = kernel taps | lines * (len + 2r) samples
+__global__ void __launch_bounds__(GA_THREADS) k_gauss_x(const __grid_constant__ GaussArgs a) {
+    const int len = a.dims[0], r = a.r, w = len + 2 * r;
+    float* kt = ga_sm;
+    float* buf = ga_sm + (2 * r + 1);
+    for (int i = threadIdx.x; i < 2 * r + 1; i += blockDim.x) kt[i] = a.kern[i];
+    const long long nrows = (long long)a.dims[1] * a.dims[2];
+    const long long row0 = (long long)blockIdx.x * a.lines;
+    const int nl = (int)min((long long)a.lines, nrows - row0);
+    for (int i = threadIdx.x; i < nl * w; i += blockDim.x) {
+        const int l = i / w, p = i - l * w;
+        buf[i] = a.in[(row0 + l) * len + mirror_single(p - r, len)];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nl * len; i += blockDim.x) {
+        const int l = i / len, x = i - l * len;
+        const float* b = buf + l * w + x;
+        float s = 0.f;
+        for (int t = 0; t <= 2 * r; ++t) s = fmaf(kt[t], b[t], s);
+        a.out[(row0 + l) * len + x] = s;
+    }
+}
+
+// y / z pass: CTA owns a column block of 32 x-values for a fixed index of the third axis
+__global__ void __launch_bounds__(GA_THREADS) k_gauss_strided(const __grid_constant__ GaussArgs a) {
+    const int len = a.dims[a.axis], r = a.r;
+    float* kt = ga_sm;
+    float* buf = ga_sm + (2 * r + 1);  // [len + 2r][32]
+    for (int i = threadIdx.x; i < 2 * r + 1; i += blockDim.x) kt[i] = a.kern[i];
+    const int x0 = blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5, nwy = blockDim.x >> 5;
+    const int x = x0 + lane;
+    const long long sx = 1, sy = a.dims[0], sz = (long long)a.dims[0] * a.dims[1];
+    const long long stride = a.axis == 1 ? sy : sz;
+    const long long base = (a.axis == 1 ? (long long)blockIdx.y * sz : (long long)blockIdx.y * sy) + x * sx;
+    const bool ok = x < a.dims[0];
+    for (int p = wy; p < len + 2 * r; p += nwy)
+        buf[p * 32 + lane] = ok ? a.in[base + (long long)mirror_single(p - r, len) * stride] : 0.f;
+    __syncthreads();
+    if (!ok) return;
+    for (int o = wy; o < len; o += nwy) {
+        const float* b = buf + o * 32 + lane;
+        float s = 0.f;
+        for (int t = 0; t <= 2 * r; ++t) s = fmaf(kt[t], b[t * 32], s);
+        a.out[base + (long long)o * stride] = s;
+    }
+}
+
+__global__ void k_to_float(const void* in, int dtype, float* out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long st = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += st) {
+        float v;
+        if (dtype == BS_DTYPE_U16) v = (float)((const unsigned short*)in)[i];
+        else if (dtype == BS_DTYPE_F32) v = ((const float*)in)[i];
+        else v = (float)((const unsigned char*)in)[i];
+        out[i] = v;
+    }
+}
+
+__global__ void k_sqdiff(const float* f, const float* g, float* out, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long st = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += st) {
+        const float d = f[i] - g[i];
+        out[i] = d * d;
+    }
+}
+
+static std::vector<float> gauss_kernel(double sigma, int* r_out) {
+    const int size = std::max(2, (int)(3.0 * sigma + 0.5) + 1);
+    const int r = size - 1;
+    std::vector<double> k(2 * r + 1);
+    double sum = 0.0;
+    for (int i = -r; i <= r; ++i) {
+        k[i + r] = std::exp(-0.5 * ((double)i / sigma) * ((double)i / sigma));
+        sum += k[i + r];
+    }
+    std::vector<float> out(2 * r + 1);
+    for (size_t i = 0; i < k.size(); ++i) out[i] = (float)(k[i] / sum);
+    *r_out = r;
+    return out;
+}
+
+// gaussian blur src -> dst using tmp (all float volumes of `dims`); order x, y, z
+static int gauss3(bs_ctx* ctx, const float* src, float* dst, float* tmp, const long long dims[3], double sigma,
+                  float* kern_dev) {
+    int r;
+    std::vector<float> k = gauss_kernel(sigma, &r);
+    BS_CUDA(ctx, cudaMemcpyAsync(kern_dev, k.data(), sizeof(float) * k.size(), cudaMemcpyHostToDevice, ctx->stream));
+    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // k is a stack-lifetime staging buffer
+    GaussArgs a;
+    a.kern = kern_dev;
+    a.r = r;
+    for (int d = 0; d < 3; ++d) a.dims[d] = (int)dims[d];
+    // x: src -> dst
+    {
+        const size_t per_line = (size_t)(dims[0] + 2 * r) * sizeof(float);
+        const size_t fixed = (size_t)(2 * r + 1) * sizeof(float);
+        int lines = (int)std::min<size_t>(8, (GA_SMEM_MAX - fixed) / per_line);
+        if (lines < 1) return bs_set_error(ctx, BS_ERR_UNSUPPORTED, "content: x size too large for shared memory");
+        a.in = src; a.out = dst; a.axis = 0; a.lines = lines;
+        const long long nrows = dims[1] * dims[2];
+        bs_launch_scope sc(ctx, "content_gauss");
+        k_gauss_x<<<(unsigned)((nrows + lines - 1) / lines), GA_THREADS, fixed + lines * per_line, ctx->stream>>>(a);
+    }
+    BS_CUDA(ctx, cudaGetLastError());
+    // y: dst -> tmp ; z: tmp -> dst
+    for (int axis = 1; axis <= 2; ++axis) {
+        const size_t smem = ((size_t)(2 * r + 1) + (size_t)(dims[axis] + 2 * r) * 32) * sizeof(float);
+        if (smem > GA_SMEM_MAX) return bs_set_error(ctx, BS_ERR_UNSUPPORTED, "content: axis %d too long for shared memory", axis);
+        a.in = axis == 1 ? dst : tmp;
+        a.out = axis == 1 ? tmp : dst;
+        a.axis = axis;
+        a.lines = 0;
+        dim3 grid((unsigned)((dims[0] + 31) / 32), (unsigned)(axis == 1 ? dims[2] : dims[1]), 1);
+        bs_launch_scope sc(ctx, "content_gauss");
+        k_gauss_strided<<<grid, GA_THREADS, smem, ctx->stream>>>(a);
+    }
+    BS_CUDA(ctx, cudaGetLastError());
+    return BS_OK;
+}
+
+extern "C" int bs_content_weights(bs_ctx* ctx, unsigned long long vol_handle, double sigma1, double sigma2,
+                                  unsigned long long* content_handle) {
+    if (!ctx) return BS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!content_handle || !(sigma1 > 0.0) || !(sigma2 > 0.0))
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_content_weights: bad argument");
+    auto it = ctx->vols.find(vol_handle);
+    if (it == ctx->vols.end()) return bs_set_error(ctx, BS_ERR_ARG, "bs_content_weights: unknown handle %llu", vol_handle);
+    const bs_volume src = it->second;
+    BS_CUDA(ctx, cudaSetDevice(ctx->device));
+    BS_CUDA(ctx, cudaFuncSetAttribute((const void*)k_gauss_x, cudaFuncAttributeMaxDynamicSharedMemorySize, GA_SMEM_MAX));
+    BS_CUDA(ctx, cudaFuncSetAttribute((const void*)k_gauss_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, GA_SMEM_MAX));
+    const long long n = src.dims[0] * src.dims[1] * src.dims[2];
+    float *f = nullptr, *g = nullptr, *t = nullptr, *kern = nullptr;
+    auto cleanup = [&]() {
+        if (f) cudaFree(f);
+        if (g) cudaFree(g);
+        if (t) cudaFree(t);
+        if (kern) cudaFree(kern);
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&f, sizeof(float) * n)) != cudaSuccess || (e = cudaMalloc(&g, sizeof(float) * n)) != cudaSuccess ||
+        (e = cudaMalloc(&t, sizeof(float) * n)) != cudaSuccess || (e = cudaMalloc(&kern, sizeof(float) * 65536)) != cudaSuccess) {
+        cleanup();
+        return bs_set_error(ctx, BS_ERR_NOMEM, "bs_content_weights: cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    const int blocks = ctx->sm_count * 8;
+    int rc = BS_OK;
+    {
+        bs_launch_scope sc(ctx, "content_misc");
+        k_to_float<<<blocks, 256, 0, ctx->stream>>>(src.dev, src.dtype, f, n);
+    }
+    if (3.0 * std::max(sigma1, sigma2) + 2 > 30000) rc = bs_set_error(ctx, BS_ERR_ARG, "bs_content_weights: sigma too large");
+    if (!rc) rc = gauss3(ctx, f, g, t, src.dims, sigma1, kern);
+    if (!rc) {
+        bs_launch_scope sc(ctx, "content_misc");
+        k_sqdiff<<<blocks, 256, 0, ctx->stream>>>(f, g, f, n);
+    }
+    if (!rc) rc = gauss3(ctx, f, g, t, src.dims, sigma2, kern);
+    if (!rc) {
+        e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = bs_set_error(ctx, BS_ERR_CUDA, "bs_content_weights: %s", cudaGetErrorString(e));
+    }
+    if (rc) {
+        cudaStreamSynchronize(ctx->stream);
+        cleanup();
+        return rc;
+    }
+    cudaFree(f);
+    cudaFree(t);
+    cudaFree(kern);
+    bs_volume v;
+    v.dev = g;
+    v.dims[0] = src.dims[0]; v.dims[1] = src.dims[1]; v.dims[2] = src.dims[2];
+    v.dtype = BS_DTYPE_F32;
+    v.owned = true;
+    *content_handle = ctx->next_handle++;
+    ctx->vols[*content_handle] = v;
+    return BS_OK;
+}

@@ -1,0 +1,1110 @@
+// Hot path 1: phase correlation of one overlap-cropped tile pair, entirely on the device.
+// Replaces TransformationTools.computeStitching's numeric core
+// (PairwiseStitching.getShift -> PhaseCorrelation2.calculatePCM + getShift; call site
+// J/SparkPairwiseStitching.java:247-255).  No cuFFT: the 3-D real FFT is five hand-written
+// passes over an x-fastest half spectrum S[Pz][Py][pitch] (complex64, pitch = M+1 rounded up
+// to 16 so every row is 128 B aligned):
+//
+//   k_fft_x_r2c      uint16/float crop -> blended mirrored extension + zero pad -> R2C along x
+//   k_fft_strided    (mode 0) forward FFT along y, in place, both spectra in one launch
+//   k_fft_strided    (mode 1) forward z FFT of A and B, unit-magnitude normalisation,
+//                    conj(A)*B, forward z FFT of the product      [reads 2S, writes S]
+//   k_fft_strided    (mode 0) forward y FFT of the product
+//   k_fft_x_c2r      conj + C2R along x, in place -> real PCM (row pitch 2*pitch floats)
+//   k_peaks          periodic 6-neighbour local maxima, per-CTA top-K
+//   k_gather27       3x3x3 neighbourhoods of the K peaks (sub-pixel fit runs on the host)
+//   k_pearson        exact integer sums (uint64 atomics) for all surviving wrap candidates
+//
+// Inverse transforms are forward transforms of conjugated data (conj(F(conj X)) = N F^-1 X);
+// the two conjugations between consecutive passes cancel, so only the product step and the
+// C2R load conjugate.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "bs_internal.cuh"
+#include "pcm_fft.cuh"
+
+#define PCM_THREADS 256
+#define PCM_KMAX 32
+#define PCM_SMEM_MAX 232448  // 227 KB opt-in limit per CTA on sm_100
+
+extern __shared__ __align__(16) float2 bs_sm[];
+
+// ------------------------------------------------------------------------------------------
+// x pass, real -> complex
+struct XR2CArgs {
+    const void* img[2];
+    float2* spec[2];
+    int dtype;
+    int dx, dy, dz;
+    int Px, Py, Pz, M, pitch;
+    int Ey, Ez;
+    const int* idx_x; const float* w_x;
+    const int* idx_y; const float* w_y;
+    const int* idx_z; const float* w_z;
+    const float2* tw;
+    FftPlan plan;
+    int lshift;
+};
+
+__device__ __forceinline__ float load_voxel(const void* p, int dtype, size_t i) {
+    if (dtype == BS_DTYPE_U16) return (float)__ldg((const unsigned short*)p + i);
+    if (dtype == BS_DTYPE_F32) return __ldg((const float*)p + i);
+    return (float)__ldg((const unsigned char*)p + i);
+}
+
+__global__ void __launch_bounds__(PCM_THREADS) k_fft_x_r2c(const __grid_constant__ XR2CArgs a) {
+    const int LB = 1 << a.lshift, ls = LB + 1;
+    float2* tw = bs_sm;
+    float2* b0 = bs_sm + a.Px;
+    float2* b1 = b0 + a.M * ls;
+    const int zp = blockIdx.y, y0 = blockIdx.x * LB, im = blockIdx.z;
+    float2* __restrict__ spec = a.spec[im];
+    const size_t rowbase = ((size_t)zp * a.Py + y0) * a.pitch;
+    const int nlines = min(LB, a.Py - y0);
+    if (zp >= a.Ez || y0 >= a.Ey) {  // every line of this CTA lies in the zero padding
+        const float2 z2 = make_float2(0.f, 0.f);
+        for (int i = threadIdx.x; i < nlines * a.pitch; i += blockDim.x) spec[rowbase + i] = z2;
+        return;
+    }
+    for (int i = threadIdx.x; i < a.Px; i += blockDim.x) tw[i] = a.tw[i];
+    const float wz = a.w_z[zp];
+    const int sz = a.idx_z[zp];
+    const void* img = a.img[im];
+    for (int item = threadIdx.x; item < LB * a.M; item += blockDim.x) {
+        const int l = item / a.M, n = item - l * a.M;
+        float2 v = make_float2(0.f, 0.f);
+        const int yp = y0 + l;
+        if (l < nlines && yp < a.Ey) {
+            const float wy = a.w_y[yp];
+            const size_t rb = ((size_t)sz * a.dy + a.idx_y[yp]) * a.dx;
+            const int xp = 2 * n;
+            const float g0 = (a.w_x[xp] * wy) * wz, g1 = (a.w_x[xp + 1] * wy) * wz;
+            if (g0 != 0.f) v.x = load_voxel(img, a.dtype, rb + a.idx_x[xp]) * g0;
+            if (g1 != 0.f) v.y = load_voxel(img, a.dtype, rb + a.idx_x[xp + 1]) * g1;
+        }
+        b0[n * ls + l] = v;
+    }
+    __syncthreads();
+    const float2* res = fft_tile(b0, b1, tw, a.plan, a.lshift, ls, 2);
+    // untangle the packed half-length transform into the real-input spectrum X[0..M]
+    for (int item = threadIdx.x; item < nlines * a.pitch; item += blockDim.x) {
+        const int l = item / a.pitch, k = item - l * a.pitch;
+        float2 X = make_float2(0.f, 0.f);
+        if (k <= a.M) {
+            const int k0 = (k == a.M) ? 0 : k;
+            const int k1 = (k == 0 || k == a.M) ? 0 : a.M - k;
+            const float2 Zk = res[k0 * ls + l];
+            float2 Zm = res[k1 * ls + l];
+            Zm.y = -Zm.y;
+            const float2 E = make_float2(0.5f * (Zk.x + Zm.x), 0.5f * (Zk.y + Zm.y));
+            const float2 D = make_float2(0.5f * (Zk.x - Zm.x), 0.5f * (Zk.y - Zm.y));
+            const float2 wD = cmulf(tw[k], D);
+            X = make_float2(E.x + wD.y, E.y - wD.x);  // E - i*w*D
+        }
+        spec[rowbase + (size_t)l * a.pitch + k] = X;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// strided passes (y and z)
+struct StridedArgs {
+    float2* a;
+    float2* b;
+    long long estride;   // float2 units between consecutive elements along the FFT axis
+    long long ostride;   // float2 units between consecutive blockIdx.y
+    const float2* tw;
+    FftPlan plan;
+    int tshift;          // log2(tile width in float2)
+    int mode;            // 0: forward in place on (blockIdx.z ? b : a); 1: cross-power (a,b) -> a
+    float thresh;        // normalisation threshold
+};
+
+__device__ __forceinline__ void tile_load(float2* dst, const float2* g, long long estride, int N, int tshift) {
+    const int vshift = tshift - 1;           // float4 vectors per row = TW/2
+    const int vmask = (1 << vshift) - 1;
+    const int nvec = N << vshift;
+    float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const int e = i >> vshift, c = i & vmask;
+        d4[i] = __ldcg(reinterpret_cast<const float4*>(g + (long long)e * estride) + c);
+    }
+}
+
+__device__ __forceinline__ void tile_store(float2* g, const float2* src, long long estride, int N, int tshift) {
+    const int vshift = tshift - 1;
+    const int vmask = (1 << vshift) - 1;
+    const int nvec = N << vshift;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll 4
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
+        const int e = i >> vshift, c = i & vmask;
+        __stcg(reinterpret_cast<float4*>(g + (long long)e * estride) + c, s4[i]);
+    }
+}
+
+__device__ __forceinline__ float2 unit_or_zero(float2 x, float thresh) {
+    const float m = sqrtf(x.x * x.x + x.y * x.y);
+    if (m < thresh) return make_float2(0.f, 0.f);
+    return make_float2(x.x / m, x.y / m);
+}
+
+__global__ void __launch_bounds__(PCM_THREADS) k_fft_strided(const __grid_constant__ StridedArgs a) {
+    const int TW = 1 << a.tshift, N = a.plan.n;
+    const int twpad = (N + 1) & ~1;
+    float2* tw = bs_sm;
+    float2* B0 = bs_sm + twpad;
+    float2* B1 = B0 + (size_t)N * TW;
+    const size_t base = (size_t)blockIdx.y * a.ostride + (size_t)blockIdx.x * TW;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = a.tw[i];
+    if (a.mode == 0) {
+        float2* g = (blockIdx.z ? a.b : a.a) + base;
+        tile_load(B0, g, a.estride, N, a.tshift);
+        __syncthreads();
+        const float2* res = fft_tile(B0, B1, tw, a.plan, a.tshift, TW, 1);
+        tile_store(g, res, a.estride, N, a.tshift);
+    } else {
+        float2* B2 = B1 + (size_t)N * TW;
+        tile_load(B0, a.a + base, a.estride, N, a.tshift);
+        tile_load(B1, a.b + base, a.estride, N, a.tshift);
+        __syncthreads();
+        float2* rA = fft_tile(B0, B2, tw, a.plan, a.tshift, TW, 1);
+        float2* freeA = (rA == B0) ? B2 : B0;
+        float2* rB = fft_tile(B1, freeA, tw, a.plan, a.tshift, TW, 1);
+        float2* free2 = (rB == B1) ? freeA : B1;
+        const int tot = N * TW;
+        for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+            const float2 x = unit_or_zero(rA[i], a.thresh);
+            const float2 y = unit_or_zero(rB[i], a.thresh);
+            rA[i] = make_float2(x.x * y.x + x.y * y.y, x.x * y.y - x.y * y.x);  // conj(x) * y
+        }
+        __syncthreads();
+        const float2* rQ = fft_tile(rA, free2, tw, a.plan, a.tshift, TW, 1);
+        tile_store(a.a + base, rQ, a.estride, N, a.tshift);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// x pass, complex -> real, in place
+struct XC2RArgs {
+    float2* spec;
+    int Px, Py, Pz, M, pitch;
+    const float2* tw;
+    FftPlan plan;
+    int lshift;
+    float scale;
+};
+
+__global__ void __launch_bounds__(PCM_THREADS) k_fft_x_c2r(const __grid_constant__ XC2RArgs a) {
+    const int LB = 1 << a.lshift, ls = LB + 1;
+    float2* tw = bs_sm;
+    float2* T0 = bs_sm + a.Px;                 // (M+1) * ls
+    float2* T1 = T0 + (size_t)(a.M + 1) * ls;  // M * ls
+    const int zp = blockIdx.y, y0 = blockIdx.x * LB;
+    const size_t rowbase = ((size_t)zp * a.Py + y0) * a.pitch;
+    const int nlines = min(LB, a.Py - y0);
+    for (int i = threadIdx.x; i < a.Px; i += blockDim.x) tw[i] = a.tw[i];
+    const int M1 = a.M + 1;
+    for (int item = threadIdx.x; item < LB * M1; item += blockDim.x) {
+        const int l = item / M1, k = item - l * M1;
+        float2 v = make_float2(0.f, 0.f);
+        if (l < nlines) {
+            v = __ldcg(a.spec + rowbase + (size_t)l * a.pitch + k);
+            v.y = -v.y;  // partial inverse along y,z = conj of the forward transforms of conj data
+        }
+        T0[k * ls + l] = v;
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < a.M * LB; item += blockDim.x) {
+        const int k = item >> a.lshift, l = item & (LB - 1);
+        const float2 Xk = T0[k * ls + l];
+        float2 Xm = T0[(a.M - k) * ls + l];
+        Xm.y = -Xm.y;
+        const float2 E = make_float2(0.5f * (Xk.x + Xm.x), 0.5f * (Xk.y + Xm.y));
+        const float2 D = make_float2(0.5f * (Xk.x - Xm.x), 0.5f * (Xk.y - Xm.y));
+        float2 w = tw[k];
+        w.y = -w.y;  // e^{+2 pi i k / P}
+        const float2 O = cmulf(D, w);
+        // Z = E + i*O ; store conj(Z) (inverse via forward transform of the conjugate)
+        T1[k * ls + l] = make_float2(E.x - O.y, -(E.y + O.x));
+    }
+    __syncthreads();
+    const float2* res = fft_tile(T1, T0, tw, a.plan, a.lshift, ls, 2);
+    for (int item = threadIdx.x; item < nlines * a.M; item += blockDim.x) {
+        const int l = item / a.M, n = item - l * a.M;
+        const float2 r = res[n * ls + l];
+        float2* row = a.spec + rowbase + (size_t)l * a.pitch;
+        __stcg(row + n, make_float2(r.x * a.scale, -r.y * a.scale));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// peak search: periodic axis-neighbour local maxima, top-K per CTA
+struct PeakEntry {
+    float val;
+    int pad;
+    long long idx;
+};
+
+struct PeakArgs {
+    const float* pcm;
+    int Px, Py, Pz;
+    long long rowpitch;  // floats
+    int K;
+    PeakEntry* out;      // gridDim.x * K
+};
+
+__device__ __forceinline__ bool peak_better(float v, long long i, float v2, long long i2) {
+    return v > v2 || (v == v2 && i < i2);
+}
+
+__global__ void __launch_bounds__(PCM_THREADS) k_peaks(const __grid_constant__ PeakArgs a) {
+    float vals[PCM_KMAX];
+    long long idxs[PCM_KMAX];
+    int cnt = 0;
+    float thr = -INFINITY;  // K-th best of this thread once its list is full
+    const int K = a.K;
+    const long long nrows = (long long)a.Py * a.Pz;
+    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+        const int z = (int)(row / a.Py), y = (int)(row - (long long)z * a.Py);
+        const float* rp = a.pcm + row * a.rowpitch;
+        const float* rym = a.pcm + ((long long)z * a.Py + (y == 0 ? a.Py - 1 : y - 1)) * a.rowpitch;
+        const float* ryp = a.pcm + ((long long)z * a.Py + (y == a.Py - 1 ? 0 : y + 1)) * a.rowpitch;
+        const float* rzm = a.pcm + ((long long)(z == 0 ? a.Pz - 1 : z - 1) * a.Py + y) * a.rowpitch;
+        const float* rzp = a.pcm + ((long long)(z == a.Pz - 1 ? 0 : z + 1) * a.Py + y) * a.rowpitch;
+        for (int x = threadIdx.x; x < a.Px; x += blockDim.x) {
+            const float v = rp[x];
+            if (!(v > thr)) continue;  // later index loses ties; also drops NaN
+            if (v < rp[x == 0 ? a.Px - 1 : x - 1] || v < rp[x == a.Px - 1 ? 0 : x + 1]) continue;
+            if (v < rym[x] || v < ryp[x] || v < rzm[x] || v < rzp[x]) continue;
+            const long long li = row * a.Px + x;
+            int pos = cnt < K ? cnt : K - 1;
+            while (pos > 0 && vals[pos - 1] < v) {
+                vals[pos] = vals[pos - 1];
+                idxs[pos] = idxs[pos - 1];
+                --pos;
+            }
+            vals[pos] = v;
+            idxs[pos] = li;
+            if (cnt < K) ++cnt;
+            if (cnt == K) thr = vals[K - 1];
+        }
+    }
+    // K rounds of block arg-max over the heads of the per-thread sorted lists
+    __shared__ float s_v[PCM_THREADS / 32];
+    __shared__ long long s_i[PCM_THREADS / 32];
+    __shared__ int s_t[PCM_THREADS / 32];
+    __shared__ int s_win;
+    int head = 0;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int round = 0; round < K; ++round) {
+        float v = head < cnt ? vals[head] : -INFINITY;
+        long long li = head < cnt ? idxs[head] : 0x7fffffffffffffffLL;
+        int t = threadIdx.x;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float v2 = __shfl_down_sync(0xffffffffu, v, off);
+            const long long i2 = __shfl_down_sync(0xffffffffu, li, off);
+            const int t2 = __shfl_down_sync(0xffffffffu, t, off);
+            if (peak_better(v2, i2, v, li)) { v = v2; li = i2; t = t2; }
+        }
+        if (lane == 0) { s_v[wid] = v; s_i[wid] = li; s_t[wid] = t; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float bv = s_v[0];
+            long long bi = s_i[0];
+            int bt = s_t[0];
+            for (int w = 1; w < PCM_THREADS / 32; ++w)
+                if (peak_better(s_v[w], s_i[w], bv, bi)) { bv = s_v[w]; bi = s_i[w]; bt = s_t[w]; }
+            PeakEntry e;
+            e.val = bv;
+            e.pad = 0;
+            e.idx = (bv == -INFINITY) ? -1 : bi;
+            a.out[(size_t)blockIdx.x * K + round] = e;
+            s_win = (bv == -INFINITY) ? -1 : bt;
+        }
+        __syncthreads();
+        if (s_win == (int)threadIdx.x) ++head;
+        __syncthreads();
+    }
+}
+
+struct GatherArgs {
+    const float* pcm;
+    int Px, Py, Pz;
+    long long rowpitch;
+    int K;
+    const long long* idx;  // K linear indices (z*Py + y)*Px + x, or -1
+    float* out;            // K * 27
+};
+
+__global__ void k_gather27(const __grid_constant__ GatherArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.K * 27) return;
+    const int p = t / 27, o = t - p * 27;
+    const long long li = a.idx[p];
+    if (li < 0) { a.out[t] = 0.f; return; }
+    const int x = (int)(li % a.Px);
+    const long long r = li / a.Px;
+    const int y = (int)(r % a.Py), z = (int)(r / a.Py);
+    const int dz = o / 9 - 1, dy = (o / 3) % 3 - 1, dx = o % 3 - 1;
+    const int xx = (x + dx + a.Px) % a.Px, yy = (y + dy + a.Py) % a.Py, zz = (z + dz + a.Pz) % a.Pz;
+    a.out[t] = a.pcm[((long long)zz * a.Py + yy) * a.rowpitch + xx];
+}
+
+// ------------------------------------------------------------------------------------------
+// Pearson sums for all candidate shifts in one launch
+struct PearsonCand {
+    int o1[3], o2[3], sz[3];
+    int pad;
+};
+
+struct PearsonArgs {
+    const void* img1;
+    const void* img2;
+    int dtype;
+    int dx, dy, dz;
+    const PearsonCand* cands;
+    unsigned long long* sums_u;  // 5 per candidate: sa, sb, saa, sbb, sab
+    double* sums_d;              // same for float input
+};
+
+template <typename T>
+__device__ __forceinline__ void pearson_int(const PearsonArgs& a, const PearsonCand& c, unsigned long long* out) {
+    const T* __restrict__ i1 = (const T*)a.img1;
+    const T* __restrict__ i2 = (const T*)a.img2;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    unsigned long long sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
+    const long long rows = (long long)c.sz[1] * c.sz[2];
+    for (long long r = (long long)blockIdx.x * nw + wid; r < rows; r += (long long)gridDim.x * nw) {
+        const int zz = (int)(r / c.sz[1]), yy = (int)(r - (long long)zz * c.sz[1]);
+        const T* p1 = i1 + ((size_t)(zz + c.o1[2]) * a.dy + (yy + c.o1[1])) * a.dx + c.o1[0];
+        const T* p2 = i2 + ((size_t)(zz + c.o2[2]) * a.dy + (yy + c.o2[1])) * a.dx + c.o2[0];
+        unsigned int ra = 0, rb = 0;
+#pragma unroll 4
+        for (int x = lane; x < c.sz[0]; x += 32) {
+            const unsigned int va = __ldg(p1 + x), vb = __ldg(p2 + x);
+            ra += va;
+            rb += vb;
+            saa += (unsigned long long)(va * va);
+            sbb += (unsigned long long)(vb * vb);
+            sab += (unsigned long long)(va * vb);
+        }
+        sa += ra;
+        sb += rb;
+    }
+    __shared__ unsigned long long s_acc[5];
+    if (threadIdx.x < 5) s_acc[threadIdx.x] = 0;
+    __syncthreads();
+    unsigned long long v[5] = {sa, sb, saa, sbb, sab};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        unsigned long long s = v[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+        if (lane == 0) atomicAdd(&s_acc[k], s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 5 && s_acc[threadIdx.x]) atomicAdd(out + threadIdx.x, s_acc[threadIdx.x]);
+}
+
+__device__ __forceinline__ void pearson_flt(const PearsonArgs& a, const PearsonCand& c, double* out) {
+    const float* __restrict__ i1 = (const float*)a.img1;
+    const float* __restrict__ i2 = (const float*)a.img2;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    double v[5] = {0, 0, 0, 0, 0};
+    const long long rows = (long long)c.sz[1] * c.sz[2];
+    for (long long r = (long long)blockIdx.x * nw + wid; r < rows; r += (long long)gridDim.x * nw) {
+        const int zz = (int)(r / c.sz[1]), yy = (int)(r - (long long)zz * c.sz[1]);
+        const float* p1 = i1 + ((size_t)(zz + c.o1[2]) * a.dy + (yy + c.o1[1])) * a.dx + c.o1[0];
+        const float* p2 = i2 + ((size_t)(zz + c.o2[2]) * a.dy + (yy + c.o2[1])) * a.dx + c.o2[0];
+        for (int x = lane; x < c.sz[0]; x += 32) {
+            const double va = __ldg(p1 + x), vb = __ldg(p2 + x);
+            v[0] += va; v[1] += vb; v[2] += va * va; v[3] += vb * vb; v[4] += va * vb;
+        }
+    }
+    __shared__ double s_accd[5];
+    if (threadIdx.x < 5) s_accd[threadIdx.x] = 0.0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        double s = v[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+        if (lane == 0) atomicAdd(&s_accd[k], s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) atomicAdd(out + threadIdx.x, s_accd[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(PCM_THREADS) k_pearson(const __grid_constant__ PearsonArgs a) {
+    const PearsonCand c = a.cands[blockIdx.y];
+    if (a.dtype == BS_DTYPE_U16) pearson_int<unsigned short>(a, c, a.sums_u + 5 * blockIdx.y);
+    else if (a.dtype == BS_DTYPE_U8) pearson_int<unsigned char>(a, c, a.sums_u + 5 * blockIdx.y);
+    else pearson_flt(a, c, a.sums_d + 5 * blockIdx.y);
+}
+
+// ==========================================================================================
+// host side
+// ==========================================================================================
+static const int kRadices[] = {16, 15, 12, 10, 9, 8, 6, 5, 4, 3, 2};
+
+static void plan_search(int n, int depth, int* cur, int* best, int* best_len) {
+    if (n == 1) {
+        if (depth < *best_len) {
+            *best_len = depth;
+            memcpy(best, cur, sizeof(int) * depth);
+        }
+        return;
+    }
+    if (depth + 1 >= *best_len || depth >= BS_FFT_MAX_STAGES) return;
+    for (int r : kRadices) {
+        if (n % r) continue;
+        if (depth > 0 && r > cur[depth - 1]) continue;  // non-increasing: canonical order
+        cur[depth] = r;
+        plan_search(n / r, depth + 1, cur, best, best_len);
+    }
+}
+
+static bool make_plan(int n, FftPlan* p) {
+    memset(p, 0, sizeof(*p));
+    p->n = n;
+    if (n == 1) { p->nst = 0; return true; }
+    int cur[BS_FFT_MAX_STAGES], best[BS_FFT_MAX_STAGES], best_len = BS_FFT_MAX_STAGES + 1;
+    plan_search(n, 0, cur, best, &best_len);
+    if (best_len > BS_FFT_MAX_STAGES) return false;
+    // odd radices first (conflict-free first-stage scatter), then descending
+    std::stable_sort(best, best + best_len, [](int x, int y) { return (x & 1) > (y & 1); });
+    p->nst = best_len;
+    for (int i = 0; i < best_len; ++i) p->radix[i] = best[i];
+    return true;
+}
+
+extern "C" int bs_good_fft_size(int n, int even) {
+    int m = n < 2 ? 2 : n;
+    for (;; ++m) {
+        int k = m;
+        for (int p : {2, 3, 5})
+            while (k % p == 0) k /= p;
+        if (k == 1 && (!even || m % 2 == 0)) return m;
+    }
+}
+
+static int ext_size(int d, int ext) { return d + (d < ext ? 2 * d : 2 * ext); }
+
+// per-axis source index + blending weight for every padded position (mirrors
+// oracle/pcm_oracle.py:_axis_profile; BlendedExtendedMirroredRandomAccesible2 semantics)
+static void axis_profile(int d, int ext, int P, std::vector<int>& idx, std::vector<float>& w) {
+    const int e = std::min(ext, d);
+    idx.assign(P, 0);
+    w.assign(P, 0.f);
+    const int period = std::max(2 * d - 2, 1);
+    for (int p = 0; p < P; ++p) {
+        const int s = p - e;
+        if (s < -e || s > d - 1 + e) continue;
+        const int dist = s < 0 ? -s : (s > d - 1 ? s - (d - 1) : 0);
+        int m = 0;
+        if (d > 1) {
+            m = s % period;
+            if (m < 0) m += period;
+            if (m >= d) m = period - m;
+        }
+        idx[p] = m;
+        w[p] = dist > 0 ? (float)(0.5 * (std::cos(M_PI * (double)dist / (double)e) + 1.0)) : 1.0f;
+    }
+}
+
+struct PcmGeometry {
+    int d[3], ext[3], P[3], E[3];
+    int M, pitch;
+    FftPlan plan_x, plan_y, plan_z;
+    int lshift_x;   // log2 lines per CTA in the x kernels
+    int tshift_y, tshift_z;
+    size_t smem_x_r2c, smem_x_c2r, smem_y, smem_z;
+};
+
+struct PcmDeviceTables {
+    int key[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // d[3], ext[3], P[3]
+    int* idx[3] = {nullptr, nullptr, nullptr};
+    float* w[3] = {nullptr, nullptr, nullptr};
+    float2* tw[3] = {nullptr, nullptr, nullptr};
+    int cap[3] = {0, 0, 0};
+};
+
+// one table set per context
+static PcmDeviceTables* tables_of(bs_ctx* ctx) {
+    if (!ctx->ws.tables) ctx->ws.tables = new PcmDeviceTables();
+    return (PcmDeviceTables*)ctx->ws.tables;
+}
+
+void bs_pcm_workspace_free(bs_ctx* ctx) {
+    bs_pcm_workspace& ws = ctx->ws;
+    if (ws.spec_a) cudaFree(ws.spec_a);
+    if (ws.spec_b) cudaFree(ws.spec_b);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            if (ws.crop[i][j]) cudaFree(ws.crop[i][j]);
+    if (ws.small) cudaFree(ws.small);
+    if (ws.small_host) cudaFreeHost(ws.small_host);
+    for (int i = 0; i < 2; ++i) {
+        if (ws.crop_ready[i]) cudaEventDestroy(ws.crop_ready[i]);
+        if (ws.crop_free[i]) cudaEventDestroy(ws.crop_free[i]);
+    }
+    if (ws.tables) {
+        PcmDeviceTables* t = (PcmDeviceTables*)ws.tables;
+        for (int d = 0; d < 3; ++d) {
+            if (t->idx[d]) cudaFree(t->idx[d]);
+            if (t->w[d]) cudaFree(t->w[d]);
+            if (t->tw[d]) cudaFree(t->tw[d]);
+        }
+        delete t;
+    }
+    ws = bs_pcm_workspace();
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s && *s ? atoi(s) : dflt;
+}
+
+static int pcm_geometry(bs_ctx* ctx, const long long dims[3], const int ext[3], PcmGeometry* g) {
+    for (int d = 0; d < 3; ++d) {
+        if (dims[d] <= 0 || dims[d] > 16384) return bs_set_error(ctx, BS_ERR_ARG, "pcm: dims[%d]=%lld out of range", d, dims[d]);
+        if (ext[d] < 1 || ext[d] > 4096) return bs_set_error(ctx, BS_ERR_ARG, "pcm: extension[%d]=%d out of range", d, ext[d]);
+        g->d[d] = (int)dims[d];
+        g->ext[d] = ext[d];
+        g->E[d] = ext_size(g->d[d], ext[d]);
+        g->P[d] = bs_good_fft_size(g->E[d], d == 0);
+    }
+    g->M = g->P[0] / 2;
+    g->pitch = ((g->M + 1 + 15) / 16) * 16;
+    if (!make_plan(g->M, &g->plan_x) || !make_plan(g->P[1], &g->plan_y) || !make_plan(g->P[2], &g->plan_z))
+        return bs_set_error(ctx, BS_ERR_UNSUPPORTED, "pcm: cannot plan FFT for padded size %dx%dx%d", g->P[0], g->P[1], g->P[2]);
+    // lines per CTA for the x kernels: largest power of two <= 16 that fits shared memory
+    int ls = env_int("BS_FFT_XLINES_LOG2", 4);
+    for (;; --ls) {
+        const int LB = 1 << ls;
+        g->smem_x_r2c = ((size_t)g->P[0] + 2 * (size_t)g->M * (LB + 1)) * sizeof(float2);
+        g->smem_x_c2r = ((size_t)g->P[0] + (size_t)(2 * g->M + 1) * (LB + 1)) * sizeof(float2);
+        if (g->smem_x_c2r <= PCM_SMEM_MAX && g->smem_x_r2c <= PCM_SMEM_MAX) break;
+        if (ls == 0) return bs_set_error(ctx, BS_ERR_UNSUPPORTED, "pcm: x size %d too large for shared memory", g->P[0]);
+    }
+    g->lshift_x = ls;
+    auto strided = [&](int N, int nbuf, int pref, int* tshift, size_t* smem) -> bool {
+        for (int ts = pref; ts >= 1; --ts) {
+            const size_t b = ((size_t)((N + 1) & ~1) + (size_t)nbuf * N * (1 << ts)) * sizeof(float2);
+            if (b <= PCM_SMEM_MAX) { *tshift = ts; *smem = b; return true; }
+        }
+        return false;
+    };
+    if (!strided(g->P[1], 2, env_int("BS_FFT_YTILE_LOG2", 3), &g->tshift_y, &g->smem_y) ||
+        !strided(g->P[2], 3, env_int("BS_FFT_ZTILE_LOG2", 3), &g->tshift_z, &g->smem_z))
+        return bs_set_error(ctx, BS_ERR_UNSUPPORTED, "pcm: y/z size %dx%d too large for shared memory", g->P[1], g->P[2]);
+    return BS_OK;
+}
+
+static int pcm_tables(bs_ctx* ctx, const PcmGeometry& g, PcmDeviceTables** out) {
+    PcmDeviceTables* t = tables_of(ctx);
+    *out = t;
+    int key[9] = {g.d[0], g.d[1], g.d[2], g.ext[0], g.ext[1], g.ext[2], g.P[0], g.P[1], g.P[2]};
+    if (!memcmp(key, t->key, sizeof(key))) return BS_OK;
+    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int d = 0; d < 3; ++d) {
+        const int P = g.P[d];
+        if (t->cap[d] < P) {
+            if (t->idx[d]) { cudaFree(t->idx[d]); cudaFree(t->w[d]); cudaFree(t->tw[d]); }
+            BS_CUDA(ctx, cudaMalloc(&t->idx[d], sizeof(int) * P));
+            BS_CUDA(ctx, cudaMalloc(&t->w[d], sizeof(float) * P));
+            BS_CUDA(ctx, cudaMalloc(&t->tw[d], sizeof(float2) * P));
+            t->cap[d] = P;
+        }
+        std::vector<int> idx;
+        std::vector<float> w;
+        axis_profile(g.d[d], g.ext[d], P, idx, w);
+        std::vector<float2> tw(P);
+        for (int k = 0; k < P; ++k) {
+            const double ang = -2.0 * M_PI * (double)k / (double)P;
+            tw[k] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+        }
+        BS_CUDA(ctx, cudaMemcpy(t->idx[d], idx.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
+        BS_CUDA(ctx, cudaMemcpy(t->w[d], w.data(), sizeof(float) * P, cudaMemcpyHostToDevice));
+        BS_CUDA(ctx, cudaMemcpy(t->tw[d], tw.data(), sizeof(float2) * P, cudaMemcpyHostToDevice));
+    }
+    memcpy(t->key, key, sizeof(key));
+    return BS_OK;
+}
+
+static int pcm_workspace(bs_ctx* ctx, const PcmGeometry& g) {
+    bs_pcm_workspace& ws = ctx->ws;
+    const size_t need = (size_t)g.P[2] * g.P[1] * g.pitch * sizeof(float2);
+    if (ws.spec_bytes < need) {
+        BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ws.spec_a) cudaFree(ws.spec_a);
+        if (ws.spec_b) cudaFree(ws.spec_b);
+        ws.spec_a = ws.spec_b = nullptr;
+        ws.spec_bytes = 0;
+        BS_CUDA(ctx, cudaMalloc(&ws.spec_a, need));
+        BS_CUDA(ctx, cudaMalloc(&ws.spec_b, need));
+        ws.spec_bytes = need;
+    }
+    const size_t small_need = 1 << 20;
+    if (!ws.small) {
+        BS_CUDA(ctx, cudaMalloc(&ws.small, small_need));
+        BS_CUDA(ctx, cudaHostAlloc(&ws.small_host, small_need, cudaHostAllocDefault));
+        ws.small_bytes = small_need;
+    }
+    return BS_OK;
+}
+
+static int set_smem(bs_ctx* ctx, const void* fn, size_t bytes) {
+    BS_CUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PCM_SMEM_MAX));
+    (void)bytes;
+    return BS_OK;
+}
+
+// forward pipeline up to the real PCM in ws.spec_a (row pitch 2*pitch floats)
+static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtype, const PcmGeometry& g,
+                           PcmDeviceTables* t) {
+    if (!ctx->pcm_attr_done) {
+        int rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_strided, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r, 0))) return rc;
+        ctx->pcm_attr_done = true;
+    }
+    bs_pcm_workspace& ws = ctx->ws;
+    float2* sa = (float2*)ws.spec_a;
+    float2* sb = (float2*)ws.spec_b;
+    {
+        XR2CArgs a;
+        a.img[0] = d1; a.img[1] = d2;
+        a.spec[0] = sa; a.spec[1] = sb;
+        a.dtype = dtype;
+        a.dx = g.d[0]; a.dy = g.d[1]; a.dz = g.d[2];
+        a.Px = g.P[0]; a.Py = g.P[1]; a.Pz = g.P[2]; a.M = g.M; a.pitch = g.pitch;
+        a.Ey = g.E[1]; a.Ez = g.E[2];
+        a.idx_x = t->idx[0]; a.w_x = t->w[0];
+        a.idx_y = t->idx[1]; a.w_y = t->w[1];
+        a.idx_z = t->idx[2]; a.w_z = t->w[2];
+        a.tw = t->tw[0];
+        a.plan = g.plan_x;
+        a.lshift = g.lshift_x;
+        const int LB = 1 << g.lshift_x;
+        dim3 grid((g.P[1] + LB - 1) / LB, g.P[2], 2);
+        bs_launch_scope sc(ctx, "fft_x_r2c");
+        k_fft_x_r2c<<<grid, PCM_THREADS, g.smem_x_r2c, ctx->stream>>>(a);
+    }
+    BS_CUDA(ctx, cudaGetLastError());
+    {
+        StridedArgs a;
+        a.a = sa; a.b = sb;
+        a.estride = g.pitch;
+        a.ostride = (long long)g.P[1] * g.pitch;
+        a.tw = t->tw[1];
+        a.plan = g.plan_y;
+        a.tshift = g.tshift_y;
+        a.mode = 0;
+        a.thresh = 0.f;
+        dim3 grid(g.pitch >> g.tshift_y, g.P[2], 2);
+        bs_launch_scope sc(ctx, "fft_y");
+        k_fft_strided<<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
+    }
+    BS_CUDA(ctx, cudaGetLastError());
+    {
+        StridedArgs a;
+        a.a = sa; a.b = sb;
+        a.estride = (long long)g.P[1] * g.pitch;
+        a.ostride = g.pitch;
+        a.tw = t->tw[2];
+        a.plan = g.plan_z;
+        a.tshift = g.tshift_z;
+        a.mode = 1;
+        a.thresh = 1e-5f;  // PhaseCorrelation2Util.normalizeInterval threshold
+        dim3 grid(g.pitch >> g.tshift_z, g.P[1], 1);
+        bs_launch_scope sc(ctx, "fft_z_xpower");
+        k_fft_strided<<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
+    }
+    BS_CUDA(ctx, cudaGetLastError());
+    {
+        StridedArgs a;
+        a.a = sa; a.b = sb;
+        a.estride = g.pitch;
+        a.ostride = (long long)g.P[1] * g.pitch;
+        a.tw = t->tw[1];
+        a.plan = g.plan_y;
+        a.tshift = g.tshift_y;
+        a.mode = 0;
+        a.thresh = 0.f;
+        dim3 grid(g.pitch >> g.tshift_y, g.P[2], 1);
+        bs_launch_scope sc(ctx, "fft_y_inv");
+        k_fft_strided<<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
+    }
+    BS_CUDA(ctx, cudaGetLastError());
+    {
+        XC2RArgs a;
+        a.spec = sa;
+        a.Px = g.P[0]; a.Py = g.P[1]; a.Pz = g.P[2]; a.M = g.M; a.pitch = g.pitch;
+        a.tw = t->tw[0];
+        a.plan = g.plan_x;
+        a.lshift = g.lshift_x;
+        a.scale = (float)(1.0 / ((double)g.M * (double)g.P[1] * (double)g.P[2]));
+        const int LB = 1 << g.lshift_x;
+        dim3 grid((g.P[1] + LB - 1) / LB, g.P[2], 1);
+        bs_launch_scope sc(ctx, "fft_x_c2r");
+        k_fft_x_c2r<<<grid, PCM_THREADS, g.smem_x_c2r, ctx->stream>>>(a);
+    }
+    BS_CUDA(ctx, cudaGetLastError());
+    return BS_OK;
+}
+
+static void solve3(const double H[3][3], const double rhs[3], double out[3]) {
+    const double a = H[0][0], b = H[0][1], c = H[0][2], d = H[1][0], e = H[1][1], f = H[1][2], g = H[2][0],
+                 h = H[2][1], i = H[2][2];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    out[0] = out[1] = out[2] = 0.0;
+    if (det == 0.0 || !std::isfinite(det)) return;
+    const double r0 = rhs[0], r1 = rhs[1], r2 = rhs[2];
+    const double x = (r0 * (e * i - f * h) - b * (r1 * i - f * r2) + c * (r1 * h - e * r2)) / det;
+    const double y = (a * (r1 * i - f * r2) - r0 * (d * i - f * g) + c * (d * r2 - r1 * g)) / det;
+    const double z = (a * (e * r2 - r1 * h) - b * (d * r2 - r1 * g) + r0 * (d * h - e * g)) / det;
+    if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z)) { out[0] = x; out[1] = y; out[2] = z; }
+}
+
+// quadratic sub-pixel fit on a 3x3x3 neighbourhood nb[dz+1][dy+1][dx+1]
+// (imglib2 SubpixelLocalization as used by PhaseCorrelationPeak2.calculateSubpixelLocalization)
+static void subpixel_offset(const float* nb, double out[3]) {
+    auto f = [&](int z, int y, int x) { return (double)nb[(z * 3 + y) * 3 + x]; };
+    const double c = f(1, 1, 1);
+    const double g[3] = {(f(1, 1, 2) - f(1, 1, 0)) / 2.0, (f(1, 2, 1) - f(1, 0, 1)) / 2.0, (f(2, 1, 1) - f(0, 1, 1)) / 2.0};
+    double H[3][3];
+    H[0][0] = f(1, 1, 2) - 2 * c + f(1, 1, 0);
+    H[1][1] = f(1, 2, 1) - 2 * c + f(1, 0, 1);
+    H[2][2] = f(2, 1, 1) - 2 * c + f(0, 1, 1);
+    H[0][1] = H[1][0] = (f(1, 2, 2) - f(1, 2, 0) - f(1, 0, 2) + f(1, 0, 0)) / 4.0;
+    H[0][2] = H[2][0] = (f(2, 1, 2) - f(2, 1, 0) - f(0, 1, 2) + f(0, 1, 0)) / 4.0;
+    H[1][2] = H[2][1] = (f(2, 2, 1) - f(2, 0, 1) - f(0, 2, 1) + f(0, 0, 1)) / 4.0;
+    const double rhs[3] = {-g[0], -g[1], -g[2]};
+    solve3(H, rhs, out);
+}
+
+struct HostCand {
+    long long shift[3];
+    int peak;      // index into the peak list
+    int order;     // upstream enumeration order
+    long long npx;
+    double r;
+    int slot;      // slot in the device candidate list, -1 when below min overlap
+};
+
+static double pearson_from_int_sums(const unsigned long long s[5], long long n) {
+    // n*Sxy - Sx*Sy etc. in exact 128-bit integer arithmetic, final ratio in double
+    const __int128 N = n;
+    const __int128 sa = s[0], sb = s[1], saa = s[2], sbb = s[3], sab = s[4];
+    const __int128 cov = N * sab - sa * sb;
+    const __int128 va = N * saa - sa * sa;
+    const __int128 vb = N * sbb - sb * sb;
+    if (va == 0 || vb == 0) return 0.0;  // getCorrelation: constant overlap -> 0
+    return (double)cov / (std::sqrt((double)va) * std::sqrt((double)vb));
+}
+
+static double pearson_from_dbl_sums(const double s[5], long long n) {
+    const double N = (double)n;
+    const double cov = s[4] - s[0] * s[1] / N;
+    const double va = s[2] - s[0] * s[0] / N;
+    const double vb = s[3] - s[1] * s[1] / N;
+    if (!(va > 0.0) || !(vb > 0.0)) return 0.0;
+    return cov / std::sqrt(va * vb);
+}
+
+// full pipeline on device-resident crops
+static int pcm_run(bs_ctx* ctx, const void* d1, const void* d2, const long long dims[3], int dtype,
+                   const bs_pcm_params* p, bs_pcm_result* out) {
+    memset(out, 0, sizeof(*out));
+    out->r = -INFINITY;
+    if (p->peaks_to_check < 1 || p->peaks_to_check > PCM_KMAX)
+        return bs_set_error(ctx, BS_ERR_ARG, "pcm: peaks_to_check must be in [1,%d]", PCM_KMAX);
+    if (p->interpolate_xcorr)
+        return bs_set_error(ctx, BS_ERR_UNSUPPORTED, "pcm: interpolate_xcorr is not supported (reference default false)");
+    if (dtype != BS_DTYPE_U16 && dtype != BS_DTYPE_F32 && dtype != BS_DTYPE_U8)
+        return bs_set_error(ctx, BS_ERR_ARG, "pcm: bad dtype %d", dtype);
+    PcmGeometry g;
+    int rc = pcm_geometry(ctx, dims, p->extension, &g);
+    if (rc) return rc;
+    PcmDeviceTables* t;
+    if ((rc = pcm_tables(ctx, g, &t))) return rc;
+    if ((rc = pcm_workspace(ctx, g))) return rc;
+    if ((rc = pcm_compute_pcm(ctx, d1, d2, dtype, g, t))) return rc;
+    for (int d = 0; d < 3; ++d) out->pad[d] = g.P[d];
+
+    bs_pcm_workspace& ws = ctx->ws;
+    const int K = p->peaks_to_check;
+    const int peak_ctas = std::min(ctx->sm_count * 4, g.P[1] * g.P[2]);
+    // small-buffer layout (device and pinned mirror share offsets)
+    unsigned char* dsmall = (unsigned char*)ws.small;
+    unsigned char* hsmall = (unsigned char*)ws.small_host;
+    size_t off = 0;
+    const size_t off_peaks = off; off += sizeof(PeakEntry) * (size_t)peak_ctas * K;
+    const size_t off_idx = off;   off += sizeof(long long) * PCM_KMAX;
+    const size_t off_nb = off;    off += sizeof(float) * 27 * PCM_KMAX;
+    off = (off + 15) & ~(size_t)15;
+    const size_t off_cands = off; off += sizeof(PearsonCand) * 8 * PCM_KMAX;
+    const size_t off_sums = off;  off += sizeof(unsigned long long) * 5 * 8 * PCM_KMAX;
+    if (off > ws.small_bytes) return bs_set_error(ctx, BS_ERR_NOMEM, "pcm: scratch too small");
+
+    {
+        PeakArgs a;
+        a.pcm = (const float*)ws.spec_a;
+        a.Px = g.P[0]; a.Py = g.P[1]; a.Pz = g.P[2];
+        a.rowpitch = 2LL * g.pitch;
+        a.K = K;
+        a.out = (PeakEntry*)(dsmall + off_peaks);
+        bs_launch_scope sc(ctx, "peaks");
+        k_peaks<<<peak_ctas, PCM_THREADS, 0, ctx->stream>>>(a);
+    }
+    BS_CUDA(ctx, cudaGetLastError());
+    BS_CUDA(ctx, cudaMemcpyAsync(hsmall + off_peaks, dsmall + off_peaks, sizeof(PeakEntry) * (size_t)peak_ctas * K,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<PeakEntry> peaks((PeakEntry*)(hsmall + off_peaks), (PeakEntry*)(hsmall + off_peaks) + (size_t)peak_ctas * K);
+    peaks.erase(std::remove_if(peaks.begin(), peaks.end(), [](const PeakEntry& e) { return e.idx < 0; }), peaks.end());
+    std::sort(peaks.begin(), peaks.end(), [](const PeakEntry& x, const PeakEntry& y) {
+        return x.val > y.val || (x.val == y.val && x.idx < y.idx);
+    });
+    if ((int)peaks.size() > K) peaks.resize(K);
+    const int np = (int)peaks.size();
+    if (np == 0) return BS_OK;  // found = 0
+
+    long long* hidx = (long long*)(hsmall + off_idx);
+    for (int i = 0; i < PCM_KMAX; ++i) hidx[i] = i < np ? peaks[i].idx : -1;
+    if (p->do_subpixel) {
+        BS_CUDA(ctx, cudaMemcpyAsync(dsmall + off_idx, hidx, sizeof(long long) * PCM_KMAX, cudaMemcpyHostToDevice, ctx->stream));
+        GatherArgs a;
+        a.pcm = (const float*)ws.spec_a;
+        a.Px = g.P[0]; a.Py = g.P[1]; a.Pz = g.P[2];
+        a.rowpitch = 2LL * g.pitch;
+        a.K = np;
+        a.idx = (const long long*)(dsmall + off_idx);
+        a.out = (float*)(dsmall + off_nb);
+        {
+            bs_launch_scope sc(ctx, "gather27");
+            k_gather27<<<(np * 27 + 127) / 128, 128, 0, ctx->stream>>>(a);
+        }
+        BS_CUDA(ctx, cudaGetLastError());
+        BS_CUDA(ctx, cudaMemcpyAsync(hsmall + off_nb, dsmall + off_nb, sizeof(float) * 27 * np, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+
+    // candidate expansion (PhaseCorrelation2Util.expandPeakToPossibleShifts, equal-size crops)
+    const long long n_px = (long long)g.d[0] * g.d[1] * g.d[2];
+    const long long min_px = (long long)((double)n_px * p->min_overlap_frac);
+    std::vector<HostCand> cands;
+    PearsonCand* hc = (PearsonCand*)(hsmall + off_cands);
+    int nslots = 0;
+    for (int pi = 0; pi < np; ++pi) {
+        const long long li = peaks[pi].idx;
+        const long long loc[3] = {li % g.P[0], (li / g.P[0]) % g.P[1], li / ((long long)g.P[0] * g.P[1])};
+        for (int i = 0; i < 8; ++i) {
+            HostCand c;
+            c.peak = pi;
+            c.order = pi * 8 + i;
+            c.r = -INFINITY;
+            c.npx = 0;
+            c.slot = -1;
+            bool overlap = true;
+            PearsonCand pc;
+            memset(&pc, 0, sizeof(pc));
+            long long npx = 1;
+            for (int d = 0; d < 3; ++d) {
+                long long s = loc[d];
+                if (((i >> d) & 1) == 0) s = s < 0 ? s + g.P[d] : s - g.P[d];
+                c.shift[d] = s;
+                const long long n = g.d[d];
+                if (s >= 0) {
+                    if (s >= n) { overlap = false; continue; }
+                    pc.o1[d] = (int)s; pc.o2[d] = 0; pc.sz[d] = (int)std::min(n - s, n);
+                } else {
+                    if (s <= -n) { overlap = false; continue; }
+                    pc.o1[d] = 0; pc.o2[d] = (int)-s; pc.sz[d] = (int)std::min(n + s, n);
+                }
+                npx *= pc.sz[d];
+            }
+            if (overlap && npx >= min_px) {
+                c.npx = npx;
+                c.slot = nslots;
+                hc[nslots++] = pc;
+            }
+            cands.push_back(c);
+        }
+    }
+    out->n_candidates = nslots;
+    unsigned long long* hsums = (unsigned long long*)(hsmall + off_sums);
+    if (nslots > 0) {
+        BS_CUDA(ctx, cudaMemcpyAsync(dsmall + off_cands, hc, sizeof(PearsonCand) * nslots, cudaMemcpyHostToDevice, ctx->stream));
+        BS_CUDA(ctx, cudaMemsetAsync(dsmall + off_sums, 0, sizeof(unsigned long long) * 5 * nslots, ctx->stream));
+        PearsonArgs a;
+        a.img1 = d1; a.img2 = d2;
+        a.dtype = dtype;
+        a.dx = g.d[0]; a.dy = g.d[1]; a.dz = g.d[2];
+        a.cands = (const PearsonCand*)(dsmall + off_cands);
+        a.sums_u = (unsigned long long*)(dsmall + off_sums);
+        a.sums_d = (double*)(dsmall + off_sums);
+        const long long rows = (long long)g.d[1] * g.d[2];
+        const int ctas = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)ctx->sm_count * 8));
+        dim3 grid(ctas, nslots, 1);
+        {
+            bs_launch_scope sc(ctx, "pearson");
+            k_pearson<<<grid, PCM_THREADS, 0, ctx->stream>>>(a);
+        }
+        BS_CUDA(ctx, cudaGetLastError());
+        BS_CUDA(ctx, cudaMemcpyAsync(hsums, dsmall + off_sums, sizeof(unsigned long long) * 5 * nslots, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& c : cands) {
+        if (c.slot < 0) continue;
+        if (dtype == BS_DTYPE_F32) c.r = pearson_from_dbl_sums((const double*)hsums + 5 * c.slot, c.npx);
+        else c.r = pearson_from_int_sums(hsums + 5 * c.slot, c.npx);
+    }
+    // Collections.sort(peaks, reverseOrder(by crossCorr, then nPixel)) -- stable
+    std::stable_sort(cands.begin(), cands.end(), [](const HostCand& x, const HostCand& y) {
+        if (x.r != y.r) return x.r > y.r;
+        return x.npx > y.npx;
+    });
+    const HostCand& best = cands[0];
+    if (std::isinf(best.r)) return BS_OK;  // found = 0
+    out->found = 1;
+    out->r = best.r;
+    out->n_overlap_px = best.npx;
+    const long long li = peaks[best.peak].idx;
+    out->peak_index[0] = li % g.P[0];
+    out->peak_index[1] = (li / g.P[0]) % g.P[1];
+    out->peak_index[2] = li / ((long long)g.P[0] * g.P[1]);
+    out->pcm_value = peaks[best.peak].val;
+    double sub[3] = {0, 0, 0};
+    if (p->do_subpixel) subpixel_offset((const float*)(hsmall + off_nb) + 27 * best.peak, sub);
+    for (int d = 0; d < 3; ++d) {
+        out->shift_int[d] = best.shift[d];
+        out->shift_sub[d] = (double)best.shift[d] + sub[d];
+    }
+    return BS_OK;
+}
+
+static size_t crop_bytes_of(const long long dims[3], int dtype) {
+    const size_t es = dtype == BS_DTYPE_U16 ? 2 : dtype == BS_DTYPE_F32 ? 4 : 1;
+    return (size_t)dims[0] * dims[1] * dims[2] * es;
+}
+
+static int ensure_crop_buffers(bs_ctx* ctx, size_t bytes, int nbuf) {
+    bs_pcm_workspace& ws = ctx->ws;
+    if (ws.crop_bytes >= bytes && ws.crop[0][0] && (nbuf < 2 || ws.crop[1][0])) return BS_OK;
+    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    BS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    const size_t nb = std::max(bytes, ws.crop_bytes);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+            if (ws.crop[i][j]) cudaFree(ws.crop[i][j]);
+            ws.crop[i][j] = nullptr;
+        }
+    ws.crop_bytes = 0;
+    for (int i = 0; i < nbuf; ++i)
+        for (int j = 0; j < 2; ++j) BS_CUDA(ctx, cudaMalloc(&ws.crop[i][j], nb));
+    for (int i = 0; i < 2; ++i) {
+        if (!ws.crop_ready[i]) BS_CUDA(ctx, cudaEventCreateWithFlags(&ws.crop_ready[i], cudaEventDisableTiming));
+        if (!ws.crop_free[i]) BS_CUDA(ctx, cudaEventCreateWithFlags(&ws.crop_free[i], cudaEventDisableTiming));
+    }
+    ws.crop_bytes = nb;
+    return BS_OK;
+}
+
+extern "C" {
+
+void bs_pcm_default_params(bs_pcm_params* p) {
+    if (!p) return;
+    p->peaks_to_check = 5;
+    p->do_subpixel = 1;
+    p->interpolate_xcorr = 0;
+    p->min_overlap_frac = 0.25;
+    p->extension[0] = p->extension[1] = p->extension[2] = 10;
+}
+
+int bs_pcm_pair(bs_ctx* ctx, const void* img1, const void* img2, const long long dims[3], int dtype,
+                const bs_pcm_params* params, int on_device, bs_pcm_result* out) {
+    if (!ctx) return BS_ERR_ARG;
+    const void* a1[1] = {img1};
+    const void* a2[1] = {img2};
+    return bs_pcm_batch(ctx, 1, a1, a2, dims, dtype, params, on_device, out);
+}
+
+int bs_pcm_batch(bs_ctx* ctx, int n, const void* const* img1, const void* const* img2, const long long* dims,
+                 int dtype, const bs_pcm_params* params, int on_device, bs_pcm_result* out) {
+    if (!ctx) return BS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n < 0 || (n > 0 && (!img1 || !img2 || !dims || !params || !out)))
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_pcm_batch: NULL argument");
+    BS_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (int i = 0; i < n; ++i) {
+        if (!img1[i] || !img2[i]) return bs_set_error(ctx, BS_ERR_ARG, "bs_pcm_batch: pair %d has a NULL image", i);
+        for (int d = 0; d < 3; ++d)
+            if (dims[3 * i + d] <= 0) return bs_set_error(ctx, BS_ERR_ARG, "bs_pcm_batch: pair %d has dims[%d] <= 0", i, d);
+    }
+    if (on_device) {
+        for (int i = 0; i < n; ++i) {
+            int rc = pcm_run(ctx, img1[i], img2[i], dims + 3 * i, dtype, params, out + i);
+            if (rc) return rc;
+        }
+        return BS_OK;
+    }
+    // host inputs: double-buffered H2D on the copy stream, overlapped with the previous pair
+    size_t maxb = 0;
+    for (int i = 0; i < n; ++i) maxb = std::max(maxb, crop_bytes_of(dims + 3 * i, dtype));
+    int rc = ensure_crop_buffers(ctx, maxb, n > 1 ? 2 : 1);
+    if (rc) return rc;
+    bs_pcm_workspace& ws = ctx->ws;
+    auto enqueue_copy = [&](int i) -> int {
+        const int b = i & 1;
+        const size_t bytes = crop_bytes_of(dims + 3 * i, dtype);
+        if (i >= 2) BS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ws.crop_free[b], 0));
+        BS_CUDA(ctx, cudaMemcpyAsync(ws.crop[b][0], img1[i], bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BS_CUDA(ctx, cudaMemcpyAsync(ws.crop[b][1], img2[i], bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        BS_CUDA(ctx, cudaEventRecord(ws.crop_ready[b], ctx->copy_stream));
+        return BS_OK;
+    };
+    if (n > 0 && (rc = enqueue_copy(0))) return rc;
+    for (int i = 0; i < n; ++i) {
+        const int b = i & 1;
+        if (i + 1 < n && (rc = enqueue_copy(i + 1))) return rc;
+        BS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ws.crop_ready[b], 0));
+        rc = pcm_run(ctx, ws.crop[b][0], ws.crop[b][1], dims + 3 * i, dtype, params, out + i);
+        if (rc) return rc;
+        BS_CUDA(ctx, cudaEventRecord(ws.crop_free[b], ctx->stream));
+    }
+    return BS_OK;
+}
+
+int bs_pcm_debug_pcm(bs_ctx* ctx, const void* img1, const void* img2, const long long dims[3], int dtype,
+                     const int extension[3], float* out_pcm, int pad_out[3]) {
+    if (!ctx) return BS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!img1 || !img2 || !dims || !extension || !out_pcm)
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_pcm_debug_pcm: NULL argument");
+    BS_CUDA(ctx, cudaSetDevice(ctx->device));
+    PcmGeometry g;
+    int rc = pcm_geometry(ctx, dims, extension, &g);
+    if (rc) return rc;
+    PcmDeviceTables* t;
+    if ((rc = pcm_tables(ctx, g, &t))) return rc;
+    if ((rc = pcm_workspace(ctx, g))) return rc;
+    const size_t bytes = crop_bytes_of(dims, dtype);
+    if ((rc = ensure_crop_buffers(ctx, bytes, 1))) return rc;
+    bs_pcm_workspace& ws = ctx->ws;
+    BS_CUDA(ctx, cudaMemcpyAsync(ws.crop[0][0], img1, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    BS_CUDA(ctx, cudaMemcpyAsync(ws.crop[0][1], img2, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = pcm_compute_pcm(ctx, ws.crop[0][0], ws.crop[0][1], dtype, g, t))) return rc;
+    BS_CUDA(ctx, cudaMemcpy2DAsync(out_pcm, sizeof(float) * g.P[0], ws.spec_a, sizeof(float2) * g.pitch,
+                                   sizeof(float) * g.P[0], (size_t)g.P[1] * g.P[2], cudaMemcpyDeviceToHost, ctx->stream));
+    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (pad_out) for (int d = 0; d < 3; ++d) pad_out[d] = g.P[d];
+    return BS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,237 @@
+// Shared-memory mixed-radix Stockham FFT building blocks (sm_100a, no cuFFT).
+//
+// A "tile" is N complex elements x L lines held in shared memory with the LINE index
+// innermost: element e of line l lives at buf[e * lstride + l].  Every butterfly therefore
+// touches, for a half-warp, 16 consecutive float2 (128 B) -> bank-conflict free for any
+// radix/stride, and for the strided (y / z) passes the tile is a verbatim copy of the global
+// layout (x-fastest spectrum rows), so loads/stores are straight 16 B-vector copies.
+//
+// Radix-R butterflies (R in {2,3,4,5,6,8,9,10,12,15,16}) are fully unrolled in registers;
+// composite radices are built at compile time by a Cooley-Tukey split with constexpr
+// twiddles, so a 540-point transform needs only 3 shared-memory round trips (9 x 10 x 6).
+#pragma once
+#include <cuda_runtime.h>
+#include <utility>
+
+#define BS_FFT_MAX_STAGES 12
+
+struct FftPlan {
+    int n;
+    int nst;
+    int radix[BS_FFT_MAX_STAGES];
+};
+
+// ------------------------------------------------------------------ compile-time trigonometry
+namespace cx {
+constexpr double pi = 3.141592653589793238462643383279502884;
+constexpr double sin_series(double x) {  // |x| <= pi/2
+    double x2 = x * x, term = x, sum = x;
+    for (int i = 1; i < 16; ++i) {
+        term *= -x2 / ((2.0 * i) * (2.0 * i + 1.0));
+        sum += term;
+    }
+    return sum;
+}
+constexpr double cos_series(double x) {
+    double x2 = x * x, term = 1.0, sum = 1.0;
+    for (int i = 1; i < 16; ++i) {
+        term *= -x2 / ((2.0 * i - 1.0) * (2.0 * i));
+        sum += term;
+    }
+    return sum;
+}
+// cos / sin of 2*pi*t/r, exact at multiples of a quarter turn
+constexpr double cos2pi(int t, int r) {
+    t %= r;
+    if (t < 0) t += r;
+    if ((4 * t) % r == 0) {
+        int q = (4 * t) / r;
+        return q == 0 ? 1.0 : q == 2 ? -1.0 : 0.0;
+    }
+    double a = 2.0 * pi * t / r;      // (0, 2pi)
+    if (a > pi) a = 2.0 * pi - a;     // cos even around pi
+    if (a > pi / 2) return -cos_series(pi - a);
+    return cos_series(a);
+}
+constexpr double sin2pi(int t, int r) {
+    t %= r;
+    if (t < 0) t += r;
+    if ((4 * t) % r == 0) {
+        int q = (4 * t) / r;
+        return q == 1 ? 1.0 : q == 3 ? -1.0 : 0.0;
+    }
+    double a = 2.0 * pi * t / r;
+    double sgn = 1.0;
+    if (a > pi) { a = 2.0 * pi - a; sgn = -1.0; }
+    if (a > pi / 2) a = pi - a;
+    return sgn * sin_series(a);
+}
+constexpr int pick_factor(int r) {
+    // split composite radices into (A, r/A): prefer 4 for 8/12/16, else smallest prime
+    if (r % 4 == 0 && r > 4) return 4;
+    if (r % 2 == 0) return 2;
+    if (r % 3 == 0) return 3;
+    if (r % 5 == 0) return 5;
+    return r;
+}
+}  // namespace cx
+
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i / +i
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+__device__ __forceinline__ float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }
+
+// v * W_R^T (forward twiddle e^{-2 pi i T / R}) with T, R compile-time
+template <int T, int R>
+__device__ __forceinline__ float2 mul_w(float2 v) {
+    constexpr int t = ((T % R) + R) % R;
+    if constexpr (t == 0) {
+        return v;
+    } else if constexpr ((4 * t) % R == 0) {
+        constexpr int q = (4 * t) / R;
+        if constexpr (q == 1) return mul_mi(v);
+        else if constexpr (q == 2) return make_float2(-v.x, -v.y);
+        else return mul_pi(v);
+    } else {
+        constexpr float c = (float)cx::cos2pi(t, R);
+        constexpr float s = (float)(-cx::sin2pi(t, R));
+        return make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void dft(float2 (&x)[R]);
+
+template <int R, int A, int... I>
+__device__ __forceinline__ void apply_inner_twiddles(float2 (&t)[R], std::integer_sequence<int, I...>) {
+    // t index I = n2 * A + k1  ->  multiply by W_R^(n2 * k1)
+    ((t[I] = mul_w<(I / A) * (I % A), R>(t[I])), ...);
+}
+
+template <int R>
+__device__ __forceinline__ void dft(float2 (&x)[R]) {
+    if constexpr (R == 1) {
+    } else if constexpr (R == 2) {
+        float2 a = x[0], b = x[1];
+        x[0] = caddf(a, b);
+        x[1] = csubf(a, b);
+    } else if constexpr (R == 3) {
+        constexpr float s = (float)cx::sin2pi(1, 3);
+        float2 t1 = caddf(x[1], x[2]);
+        float2 t2 = make_float2(x[0].x - 0.5f * t1.x, x[0].y - 0.5f * t1.y);
+        float2 d = csubf(x[1], x[2]);
+        float2 t3 = make_float2(s * d.x, s * d.y);
+        x[0] = caddf(x[0], t1);
+        x[1] = caddf(t2, mul_mi(t3));
+        x[2] = caddf(t2, mul_pi(t3));
+    } else if constexpr (R == 4) {
+        float2 a = caddf(x[0], x[2]), b = csubf(x[0], x[2]);
+        float2 c = caddf(x[1], x[3]), d = csubf(x[1], x[3]);
+        x[0] = caddf(a, c);
+        x[2] = csubf(a, c);
+        x[1] = caddf(b, mul_mi(d));
+        x[3] = caddf(b, mul_pi(d));
+    } else if constexpr (R == 5) {
+        constexpr float c1 = (float)cx::cos2pi(1, 5), c2 = (float)cx::cos2pi(2, 5);
+        constexpr float s1 = (float)cx::sin2pi(1, 5), s2 = (float)cx::sin2pi(2, 5);
+        float2 t1 = caddf(x[1], x[4]), t2 = caddf(x[2], x[3]);
+        float2 t3 = csubf(x[1], x[4]), t4 = csubf(x[2], x[3]);
+        float2 a1 = make_float2(x[0].x + c1 * t1.x + c2 * t2.x, x[0].y + c1 * t1.y + c2 * t2.y);
+        float2 a2 = make_float2(x[0].x + c2 * t1.x + c1 * t2.x, x[0].y + c2 * t1.y + c1 * t2.y);
+        float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+        float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+        x[0] = caddf(x[0], caddf(t1, t2));
+        x[1] = caddf(a1, mul_mi(b1));
+        x[4] = caddf(a1, mul_pi(b1));
+        x[2] = caddf(a2, mul_mi(b2));
+        x[3] = caddf(a2, mul_pi(b2));
+    } else {
+        // Cooley-Tukey in registers: n = B*n1 + n2, k = k1 + A*k2
+        constexpr int A = cx::pick_factor(R);
+        constexpr int B = R / A;
+        static_assert(A > 1 && A < R, "unsupported radix");
+        float2 t[R];
+#pragma unroll
+        for (int n2 = 0; n2 < B; ++n2) {
+            float2 s[A];
+#pragma unroll
+            for (int n1 = 0; n1 < A; ++n1) s[n1] = x[B * n1 + n2];
+            dft<A>(s);
+#pragma unroll
+            for (int k1 = 0; k1 < A; ++k1) t[n2 * A + k1] = s[k1];
+        }
+        apply_inner_twiddles<R, A>(t, std::make_integer_sequence<int, R>{});
+#pragma unroll
+        for (int k1 = 0; k1 < A; ++k1) {
+            float2 s[B];
+#pragma unroll
+            for (int n2 = 0; n2 < B; ++n2) s[n2] = t[n2 * A + k1];
+            dft<B>(s);
+#pragma unroll
+            for (int k2 = 0; k2 < B; ++k2) x[k1 + A * k2] = s[k2];
+        }
+    }
+}
+
+// One Stockham stage of radix R over a tile: in -> out (both shared memory, element offsets
+// relative to `sm`).  tw[k * twmul] = e^{-2 pi i k / N}.  lshift = log2(lines).
+template <int R>
+__device__ __forceinline__ void fft_stage(const float2* __restrict__ in, float2* __restrict__ out,
+                                          const float2* __restrict__ tw, int N, int Ls, int lshift,
+                                          int lstride, int twmul) {
+    const int m = N / R;
+    const int nitems = m << lshift;
+    const int lmask = (1 << lshift) - 1;
+    const int twstep = (N / (Ls * R)) * twmul;
+    for (int item = threadIdx.x; item < nitems; item += blockDim.x) {
+        const int j = item >> lshift;
+        const int l = item & lmask;
+        const int k = (Ls == 1) ? 0 : (j % Ls);
+        float2 x[R];
+        const float2* p = in + j * lstride + l;
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = p[q * m * lstride];
+        if (Ls > 1) {
+            const int ts = k * twstep;
+#pragma unroll
+            for (int q = 1; q < R; ++q) x[q] = cmulf(x[q], tw[q * ts]);
+        }
+        dft<R>(x);
+        float2* o = out + ((j - k) * R + k) * lstride + l;
+#pragma unroll
+        for (int q = 0; q < R; ++q) o[q * Ls * lstride] = x[q];
+    }
+}
+
+// Forward FFT of all lines of a tile.  Ping-pongs between `a` and `b`; returns the buffer
+// holding the result (a when the stage count is even).  Ends with __syncthreads().
+__device__ __forceinline__ float2* fft_tile(float2* a, float2* b, const float2* tw, const FftPlan& plan,
+                                         int lshift, int lstride, int twmul) {
+    int Ls = 1;
+    const int N = plan.n;
+    for (int s = 0; s < plan.nst; ++s) {
+        const int r = plan.radix[s];
+        switch (r) {
+            case 2: fft_stage<2>(a, b, tw, N, Ls, lshift, lstride, twmul); break;
+            case 3: fft_stage<3>(a, b, tw, N, Ls, lshift, lstride, twmul); break;
+            case 4: fft_stage<4>(a, b, tw, N, Ls, lshift, lstride, twmul); break;
+            case 5: fft_stage<5>(a, b, tw, N, Ls, lshift, lstride, twmul); break;
+            case 6: fft_stage<6>(a, b, tw, N, Ls, lshift, lstride, twmul); break;
+            case 8: fft_stage<8>(a, b, tw, N, Ls, lshift, lstride, twmul); break;
+            case 9: fft_stage<9>(a, b, tw, N, Ls, lshift, lstride, twmul); break;
+            case 10: fft_stage<10>(a, b, tw, N, Ls, lshift, lstride, twmul); break;
+            case 12: fft_stage<12>(a, b, tw, N, Ls, lshift, lstride, twmul); break;
+            case 15: fft_stage<15>(a, b, tw, N, Ls, lshift, lstride, twmul); break;
+            case 16: fft_stage<16>(a, b, tw, N, Ls, lshift, lstride, twmul); break;
+            default: break;
+        }
+        __syncthreads();
+        Ls *= r;
+        float2* t = a; a = b; b = t;
+    }
+    return a;
+}

@@ -1,0 +1,204 @@
+"""Host-side mirror of the reference's pairwise-stitching operator interface.
+
+Mirrors, name for name, what ``SparkPairwiseStitching``'s per-pair task calls
+(src/main/java/net/preibisch/bigstitcher/spark/SparkPairwiseStitching.java:194-303):
+
+    PairwiseStitchingParameters          (:200-202)
+    TransformationTools.computeStitching (:247-255)   -> compute_stitching
+    PairwiseStitching.getShift (upstream BigStitcher 2.5.0) -> get_shift
+    result record / filters              (:284-301, :347-380) -> PairwiseStitchingResult, filter_results
+
+Only geometry and bookkeeping happen here (overlap boxes, crops, sign conventions, result
+records); all arithmetic on voxels runs in libbsgpu.so through ``native.Context``.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .native import Context
+
+
+@dataclass
+class PairwiseStitchingParameters:
+    """net.preibisch.stitcher.algorithm.PairwiseStitchingParameters (defaults recalled:
+    minOverlap 0.25, peaksToCheck 5, doSubpixel true, interpolateCrossCorrelation false)."""
+    min_overlap: float = 0.25
+    peaks_to_check: int = 5
+    do_subpixel: bool = True
+    interpolate_cross_correlation: bool = False
+    extension: tuple = (10, 10, 10)
+
+
+@dataclass
+class PairwiseStitchingResult:
+    """Spark.SerializablePairwiseStitchingResult (J/util/Spark.java:201-233): 3x4 double
+    affine, r, bounding box min/max; ``hash`` is computed by the Java side
+    (PairwiseStitchingResult.calculateHash, J/SparkPairwiseStitching.java:287-289)."""
+    pair: tuple
+    transform: np.ndarray          # 3x4 row-packed, global coordinates
+    r: float
+    bbox_min: tuple
+    bbox_max: tuple
+    hash: float = 0.0
+    shift_px: tuple = (0.0, 0.0, 0.0)  # correction of B in (downsampled) pixel units, diagnostic
+
+
+def _overlap(min1, max1, min2, max2):
+    lo = np.maximum(min1, min2)
+    hi = np.minimum(max1, max2)
+    if np.any(hi < lo):
+        return None
+    return lo, hi
+
+
+def local_raster_overlaps(dims1_xyz, dims2_xyz, t1, t2):
+    """TransformTools.applyTranslation / getOverlap / getLocalOverlap / getLocalRasterOverlap:
+    returns (interval1_min, interval2_min, size, sub1, sub2) in xyz or None.  Raster interval
+    = ceil(min) .. floor(max) of the real local overlap; sub* = interval.min - localOverlap.min."""
+    t1 = np.asarray(t1, dtype=np.float64)
+    t2 = np.asarray(t2, dtype=np.float64)
+    d1 = np.asarray(dims1_xyz, dtype=np.float64)
+    d2 = np.asarray(dims2_xyz, dtype=np.float64)
+    ov = _overlap(t1, t1 + d1 - 1, t2, t2 + d2 - 1)
+    if ov is None:
+        return None
+    lo, hi = ov
+    l1lo, l1hi = lo - t1, hi - t1
+    l2lo, l2hi = lo - t2, hi - t2
+    i1lo, i1hi = np.ceil(l1lo - 1e-9), np.floor(l1hi + 1e-9)
+    i2lo, i2hi = np.ceil(l2lo - 1e-9), np.floor(l2hi + 1e-9)
+    s1 = i1hi - i1lo + 1
+    s2 = i2hi - i2lo + 1
+    if np.any(s1 <= 0) or np.any(s2 <= 0) or np.any(s1 != s2):
+        return None  # "0-sized or unequal overlap" -> null
+    return (i1lo.astype(np.int64), i2lo.astype(np.int64), s1.astype(np.int64), i1lo - l1lo, i2lo - l2lo)
+
+
+def get_shift(img1, img2, t1, t2, params: PairwiseStitchingParameters, ctx: Context):
+    """PairwiseStitching.getShift: phase-correlate the overlapping parts of two images
+    ([z,y,x] numpy arrays or device tensors) positioned at translations t1, t2 (xyz, pixel units
+    of the images).  Returns (shift_xyz, r) -- the correction of image 2's position relative to
+    image 1 in pixels (planted error (+3,-2,+1) is recovered as (3,-2,1))
+    -- or None ("no shift found")."""
+    dims1 = tuple(img1.shape)[::-1]
+    dims2 = tuple(img2.shape)[::-1]
+    ro = local_raster_overlaps(dims1, dims2, t1, t2)
+    if ro is None:
+        return None
+    a1, a2, size, sub1, sub2 = ro
+    c1 = img1[a1[2]:a1[2] + size[2], a1[1]:a1[1] + size[1], a1[0]:a1[0] + size[0]]
+    c2 = img2[a2[2]:a2[2] + size[2], a2[1]:a2[1] + size[1], a2[0]:a2[0] + size[0]]
+    if isinstance(c1, np.ndarray):
+        c1 = np.ascontiguousarray(c1)
+        c2 = np.ascontiguousarray(c2)
+    else:
+        c1 = c1.contiguous()
+        c2 = c2.contiguous()
+    p = ctx.pcm_params(params.peaks_to_check, params.do_subpixel, params.min_overlap, params.extension)
+    res = ctx.pcm_pair(c1, c2, p)
+    if not res.found or math.isinf(res.r):
+        return None
+    s = np.asarray(res.shift_sub if params.do_subpixel else res.shift_int, dtype=np.float64)
+    # correct for the int/real coordinate difference of the two raster crops
+    shift = s - (np.asarray(sub2) - np.asarray(sub1))
+    return shift, res.r
+
+
+def non_translations_equal(m1, m2, eps=1e-9):
+    """TransformTools.nonTranslationsEqual: the 3x3 parts agree."""
+    a = np.asarray(m1, dtype=np.float64).reshape(3, 4)[:, :3]
+    b = np.asarray(m2, dtype=np.float64).reshape(3, 4)[:, :3]
+    return bool(np.all(np.abs(a - b) < eps))
+
+
+def downsample_avg(img: np.ndarray, factors_xyz):
+    """2^k block averaging per axis (GroupedViewAggregator's remaining downsampling steps);
+    host plumbing, output float32 when any factor > 1."""
+    fx, fy, fz = (int(f) for f in factors_xyz)
+    if (fx, fy, fz) == (1, 1, 1):
+        return img
+    z, y, x = img.shape
+    z2, y2, x2 = z // fz, y // fy, x // fx
+    v = img[:z2 * fz, :y2 * fy, :x2 * fx].astype(np.float32)
+    v = v.reshape(z2, fz, y2, fy, x2, fx).mean(axis=(1, 3, 5), dtype=np.float32)
+    return v
+
+
+def compute_stitching(img_a, img_b, model_a, model_b, params: PairwiseStitchingParameters,
+                      downsample_factors=(1, 1, 1), ctx: Context | None = None):
+    """TransformationTools.computeStitching for single-view groups whose registrations differ
+    only by translation (the ``nonTranslationsEqual`` branch, J/SparkPairwiseStitching.java:216-255).
+
+    model_a / model_b: row-packed 3x4 view models (source pixel -> world).  Returns
+    ((resTransform 3x4, r), (bbox_min, bbox_max)) or None.  resTransform = M_B * T(shift*ds) *
+    M_B^-1 in global coordinates."""
+    ma = np.asarray(model_a, dtype=np.float64).reshape(3, 4)
+    mb = np.asarray(model_b, dtype=np.float64).reshape(3, 4)
+    if not non_translations_equal(ma, mb):
+        raise NotImplementedError("computeStitchingNonEqualTransformations (virtually fused views) "
+                                  "is outside this build's scope (SURVEY.md 8a row a3')")
+    ds = np.asarray(downsample_factors, dtype=np.float64)
+    a = downsample_avg(img_a, downsample_factors) if isinstance(img_a, np.ndarray) else img_a
+    b = downsample_avg(img_b, downsample_factors) if isinstance(img_b, np.ndarray) else img_b
+    # TransformTools.getInitialTransforms: translation part expressed in (downsampled) pixel units
+    lin_inv = np.linalg.inv(ma[:, :3])
+    t1 = (lin_inv @ ma[:, 3]) / ds
+    t2 = (lin_inv @ mb[:, 3]) / ds
+    # world-space overlap bounding box of the two views (BoundingBoxMaximalGroupOverlap)
+    def world_box(m, dims_xyz):
+        c = np.array([[x, y, z] for x in (0, dims_xyz[0] - 1) for y in (0, dims_xyz[1] - 1)
+                      for z in (0, dims_xyz[2] - 1)], dtype=np.float64)
+        w = c @ m[:, :3].T + m[:, 3]
+        return w.min(axis=0), w.max(axis=0)
+    full_a = tuple(img_a.shape)[::-1]
+    full_b = tuple(img_b.shape)[::-1]
+    la, ha = world_box(ma, full_a)
+    lb, hb = world_box(mb, full_b)
+    ov = _overlap(la, ha, lb, hb)
+    if ov is None:
+        return None
+    res = get_shift(a, b, t1, t2, params, ctx)
+    if res is None:
+        return None
+    shift, r = res
+    T = np.eye(4)
+    T[:3, 3] = shift * ds
+    Mb = np.vstack([mb, [0, 0, 0, 1]])
+    R = Mb @ T @ np.linalg.inv(Mb)
+    return (R[:3, :].copy(), float(r)), (tuple(ov[0]), tuple(ov[1]))
+
+
+def filter_results(results, min_r=0.3, max_r=1.0, max_shift_xyz=None, max_shift_total=None):
+    """FilteredStitchingResults with CorrelationFilter / AbsoluteShiftFilter / ShiftMagnitudeFilter
+    (J/SparkPairwiseStitching.java:347-380; defaults --minR 0.3 --maxR 1.0 :85-89)."""
+    kept = []
+    for res in results:
+        if res is None:
+            continue
+        if not (min_r <= res.r <= max_r):
+            continue
+        t = np.asarray(res.transform).reshape(3, 4)[:, 3]
+        if max_shift_xyz is not None and np.any(np.abs(t) > np.asarray(max_shift_xyz)):
+            continue
+        if max_shift_total is not None and float(np.linalg.norm(t)) > max_shift_total:
+            continue
+        kept.append(res)
+    return kept
+
+
+def stitch_pairs(pairs, tiles, models, params=None, downsample_factors=(1, 1, 1), ctx: Context | None = None):
+    """The collapsed RDD (J/SparkPairwiseStitching.java:192-312): a plain host work queue over
+    tile pairs.  ``pairs``: [(idA, idB)], ``tiles``: id -> [z,y,x] array, ``models``: id -> 3x4."""
+    params = params or PairwiseStitchingParameters()
+    out = []
+    for (ia, ib) in pairs:
+        r = compute_stitching(tiles[ia], tiles[ib], models[ia], models[ib], params, downsample_factors, ctx)
+        if r is None:
+            out.append(None)
+            continue
+        (tr, cc), (bmin, bmax) = r
+        out.append(PairwiseStitchingResult((ia, ib), tr, cc, bmin, bmax, shift_px=tuple(tr[:, 3])))
+    return out

@@ -1,0 +1,113 @@
+"""Host-side mirror of the reference interface (geometry / bookkeeping), CPU only."""
+import numpy as np
+import pytest
+
+import bsgpu
+from bsgpu import fusion, stitching
+from oracle import pcm_oracle as po
+from tests import synth
+
+
+def test_grid_create_matches_reference_usage():
+    # J/SparkAffineFusion.java:457-461: 2048^3, blockSize 128^3, blockScale 2,2,1 -> 1024 jobs
+    g = fusion.grid_create((2048, 2048, 2048), (256, 256, 128), (128, 128, 128))
+    assert len(g) == 8 * 8 * 16
+    assert g[0] == ((0, 0, 0), (256, 256, 128), (0, 0, 0))
+    assert g[1] == ((256, 0, 0), (256, 256, 128), (2, 0, 0))      # x fastest, grid pos in storage blocks
+    assert g[8] == ((0, 256, 0), (256, 256, 128), (0, 2, 0))
+    g = fusion.grid_create((300, 100, 50), (256, 256, 128), (128, 128, 128))
+    assert g == [((0, 0, 0), (256, 100, 50), (0, 0, 0)), ((256, 0, 0), (44, 100, 50), (2, 0, 0))]
+
+
+def test_adjust_all_transforms_anisotropy():
+    regs = {0: synth.translation((10, 20, 30))}
+    out = fusion.adjust_all_transforms(regs, anisotropy_factor=2.0)
+    assert np.allclose(out[0], [[1, 0, 0, 10], [0, 1, 0, 20], [0, 0, 0.5, 15]])
+    assert np.allclose(fusion.adjust_all_transforms(regs)[0], regs[0])
+
+
+def test_find_overlapping_views_expand_by_two():
+    dims = {0: (100, 100, 100), 1: (100, 100, 100)}
+    regs = {0: synth.translation((0, 0, 0)), 1: synth.translation((200, 0, 0))}
+    # view 0 spans x [0, 99]; block [101, 150] is 2 px away -> still "overlapping" (expand 2)
+    assert fusion.find_overlapping_views(dims, regs, (101, 0, 0), (150, 50, 50)) == [0]
+    assert fusion.find_overlapping_views(dims, regs, (102, 0, 0), (150, 50, 50)) == []
+    assert fusion.find_overlapping_views(dims, regs, (90, 0, 0), (210, 50, 50)) == [0, 1]
+
+
+def test_best_mipmap_level_rule():
+    res = [(1, 1, 1), (2, 2, 1), (4, 4, 2)]
+    mts = [np.array([[f[0], 0, 0, (f[0] - 1) / 2], [0, f[1], 0, (f[1] - 1) / 2], [0, 0, f[2], (f[2] - 1) / 2]], float) for f in res]
+    # full-res registration: any downsampled level would step > 1.02 px in x/y -> level 0
+    assert fusion.best_mipmap_level(synth.translation((0, 0, 0)), res, mts) == 0
+    # registration that shrinks the view by 4: level 2 steps are (1, 1, 0.5) -> accepted, best scaling
+    M = np.diag([0.25, 0.25, 0.25]) @ synth.translation((0, 0, 0))
+    assert fusion.best_mipmap_level(M, res, mts) == 2
+
+
+def test_local_raster_overlaps_integer_and_real():
+    a1, a2, size, s1, s2 = stitching.local_raster_overlaps((256, 256, 256), (256, 256, 256), (0, 0, 0), (205, 0, 0))
+    assert list(a1) == [205, 0, 0] and list(a2) == [0, 0, 0] and list(size) == [51, 256, 256]
+    a1, a2, size, s1, s2 = stitching.local_raster_overlaps((256, 256, 256), (256, 256, 256), (0, 0, 0), (204.6, 0, 0))
+    assert list(a1) == [205, 0, 0] and list(a2) == [0, 0, 0] and list(size) == [51, 256, 256]
+    assert np.allclose(s1, [0.4, 0, 0]) and np.allclose(s2, [0, 0, 0])
+    assert stitching.local_raster_overlaps((10, 10, 10), (10, 10, 10), (0, 0, 0), (10, 0, 0)) is None
+
+
+def test_filters_and_transform_equality():
+    R = stitching.PairwiseStitchingResult
+    rs = [R((0, 1), synth.translation((3, -2, 1)), 0.9, (0, 0, 0), (1, 1, 1)),
+          R((0, 2), synth.translation((1, 0, 0)), 0.2, (0, 0, 0), (1, 1, 1)),
+          R((1, 2), synth.translation((50, 0, 0)), 0.8, (0, 0, 0), (1, 1, 1)), None]
+    assert [r.pair for r in stitching.filter_results(rs)] == [(0, 1), (1, 2)]
+    assert [r.pair for r in stitching.filter_results(rs, max_shift_xyz=(10, 10, 10))] == [(0, 1)]
+    assert [r.pair for r in stitching.filter_results(rs, max_shift_total=3.0)] == []
+    assert stitching.non_translations_equal(synth.translation((1, 2, 3)), synth.translation((9, 9, 9)))
+    assert not stitching.non_translations_equal(synth.translation((1, 2, 3)), synth.rot_z(1.0))
+
+
+class _OracleCtx:
+    """Stand-in for native.Context in CPU tests of the host logic: routes pcm_pair to the
+    oracle (tests only -- the product path has no such fallback)."""
+
+    @staticmethod
+    def pcm_params(peaks, sub, mo, ext):
+        return dict(peaks_to_check=peaks, do_subpixel=sub, min_overlap_frac=mo, extension=ext)
+
+    def pcm_pair(self, a, b, p):
+        return po.pcm_shift(a, b, **p)
+
+
+def test_compute_stitching_sign_convention_config1_style():
+    """B registered at the nominal (205,0,0)-style offset but truly at
+    nominal + (3,-2,1) -> the recovered correction of B is (+3,-2,+1)."""
+    n, ov = 96, 40
+    G = synth.field((n + 16, n + 16, 2 * n + 16), seed=3, sigma=1.0)
+    A = synth.tile_from(G, (8, 8, 8), (n, n, n), 1)
+    nominal = n - ov
+    B = synth.tile_from(G, (8 + 1, 8 - 2, 8 + nominal + 3), (n, n, n), 2)
+    res = stitching.compute_stitching(A, B, synth.translation((0, 0, 0)), synth.translation((nominal, 0, 0)),
+                                      stitching.PairwiseStitchingParameters(), (1, 1, 1), _OracleCtx())
+    assert res is not None
+    (T, r), (bmin, bmax) = res
+    assert np.allclose(T[:, :3], np.eye(3))
+    assert np.allclose(T[:, 3], (3, -2, 1), atol=0.3) and np.all(np.rint(T[:, 3]) == (3, -2, 1))
+    assert r > 0.9 and bmin[0] == nominal and bmax[0] == n - 1
+
+
+def test_compute_stitching_downsampled_scales_shift_back():
+    n, ov = 96, 48
+    G = synth.field((n + 16, n + 16, 2 * n + 16), seed=4, sigma=2.0)
+    A = synth.tile_from(G, (8, 8, 8), (n, n, n), 1, noise=5)
+    nominal = n - ov
+    B = synth.tile_from(G, (8, 8 + 2, 8 + nominal - 4), (n, n, n), 2, noise=5)
+    res = stitching.compute_stitching(A, B, synth.translation((0, 0, 0)), synth.translation((nominal, 0, 0)),
+                                      stitching.PairwiseStitchingParameters(), (2, 2, 1), _OracleCtx())
+    (T, r), _ = res
+    assert np.all(np.abs(T[:, 3] - (-4, 2, 0)) <= 1.0)
+
+
+def test_compute_stitching_rejects_non_equal_linear_parts():
+    a = np.zeros((4, 4, 4), np.uint16)
+    with pytest.raises(NotImplementedError):
+        stitching.compute_stitching(a, a, synth.translation((0, 0, 0)), synth.rot_z(2.0), stitching.PairwiseStitchingParameters())

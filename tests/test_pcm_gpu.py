@@ -1,0 +1,121 @@
+"""GPU parity tests, hot path 1: libbsgpu (through the C ABI) against oracle/pcm_oracle.py.
+
+Bars (BASELINE.json north_star): integer peak / shift bit-identical; sub-pixel within 1e-3 px;
+Pearson r (exact integer sums on the device) within 1e-9.
+"""
+import numpy as np
+import pytest
+
+from oracle import pcm_oracle as po
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(ctx, a, b, **kw):
+    import bsgpu  # noqa: F401
+    ext = kw.get("extension", (10, 10, 10))
+    o = po.pcm_shift(a, b, peaks_to_check=kw.get("peaks", 5), do_subpixel=kw.get("subpixel", True),
+                     min_overlap_frac=kw.get("min_overlap", 0.25), extension=ext)
+    p = ctx.pcm_params(kw.get("peaks", 5), kw.get("subpixel", True), kw.get("min_overlap", 0.25), ext)
+    g = ctx.pcm_pair(a, b, p)
+    assert g.pad == o.pad
+    assert g.found == o.found
+    if o.found:
+        assert g.shift_int == o.shift_int, (g, o.shift_int, o.candidates[:6])
+        assert g.peak_index == o.peak_index
+        assert g.n_overlap_px == o.n_overlap_px
+        assert abs(g.r - o.r) < 1e-9
+        assert np.allclose(g.shift_sub, o.shift_sub, atol=1e-3), (g.shift_sub, o.shift_sub)
+    return g, o
+
+
+def test_pcm_volume_matches_oracle(ctx):
+    a, b = synth.shifted_pair((40, 48, 56), (3, -2, 1), seed=1)
+    pg = ctx.pcm_debug_pcm(a, b)
+    pc = po.calculate_pcm(a, b)
+    assert pg.shape == pc.shape
+    scale = np.abs(pc).max()
+    assert np.abs(pg - pc).max() < 2e-4 * scale
+    assert np.unravel_index(np.argmax(pg), pg.shape) == np.unravel_index(np.argmax(pc), pc.shape)
+
+
+@pytest.mark.parametrize("shape,shift,seed", [
+    ((64, 64, 64), (3, -2, 1), 1),
+    ((64, 64, 64), (0, 0, 0), 2),
+    ((48, 80, 96), (-7, 5, 11), 3),
+    ((96, 64, 50), (12, -9, 4), 4),
+    ((33, 45, 71), (-5, 6, -3), 5),     # odd sizes -> radix 3/5 paths, ragged line groups
+    ((128, 128, 128), (20, -20, 3), 6),
+])
+def test_planted_integer_shift(ctx, shape, shift, seed):
+    a, b = synth.shifted_pair(shape, shift, seed=seed)
+    g, o = _check(ctx, a, b)
+    assert g.found and g.shift_int == shift  # known answer, not just oracle agreement
+
+
+def test_identical_images(ctx):
+    a, _ = synth.shifted_pair((64, 64, 64), (0, 0, 0), seed=7)
+    g, o = _check(ctx, a, a.copy())
+    assert g.shift_int == (0, 0, 0) and abs(g.r - 1.0) < 1e-12
+
+
+def test_float32_input(ctx):
+    a, b = synth.shifted_pair((48, 48, 48), (4, 3, -2), seed=8, dtype=np.float32)
+    g, o = _check(ctx, a, b)
+    assert g.shift_int == (4, 3, -2)
+
+
+def test_no_subpixel_and_peak_count(ctx):
+    a, b = synth.shifted_pair((64, 64, 64), (2, 2, 2), seed=9)
+    g, o = _check(ctx, a, b, subpixel=False, peaks=1)
+    assert g.shift_sub == tuple(float(v) for v in g.shift_int)
+    _check(ctx, a, b, peaks=12)
+
+
+def test_constant_image_returns_r0(ctx):
+    a = np.full((32, 32, 32), 1000, dtype=np.uint16)
+    g, o = _check(ctx, a, a.copy())
+    if g.found:
+        assert g.r == 0.0
+
+
+def test_min_overlap_rejects_everything(ctx):
+    a, b = synth.shifted_pair((32, 32, 32), (1, 1, 1), seed=10)
+    g, o = _check(ctx, a, b, min_overlap=2.0)   # nothing can overlap by 200 %
+    assert not g.found
+
+
+def test_thin_volume_2d_like(ctx):
+    # singleton z: extension min(10, 1) = 1 -> padded size 3
+    a, b = synth.shifted_pair((1, 96, 96), (5, -4, 0), seed=11)
+    g, o = _check(ctx, a, b)
+    assert g.shift_int == (5, -4, 0)
+
+
+def test_batch_host_pipeline_equals_single(ctx):
+    pairs = [synth.shifted_pair((48, 56, 64), s, seed=20 + i) for i, s in enumerate([(1, 2, 3), (-4, 0, 2), (6, -6, 1)])]
+    single = [ctx.pcm_pair(a, b) for a, b in pairs]
+    batch = ctx.pcm_batch([p[0] for p in pairs], [p[1] for p in pairs])
+    for s, b in zip(single, batch):
+        assert s == b
+
+
+def test_device_resident_input(ctx):
+    import torch
+    a, b = synth.shifted_pair((64, 64, 64), (3, 1, -2), seed=30)
+    ta = torch.from_numpy(a.view(np.int16)).cuda()
+    tb = torch.from_numpy(b.view(np.int16)).cuda()
+    torch.cuda.synchronize()
+    g = ctx.pcm_pair(ta, tb)
+    h = ctx.pcm_pair(a, b)
+    assert g == h and g.shift_int == (3, 1, -2)
+
+
+def test_bad_arguments(ctx):
+    import bsgpu
+    a = np.zeros((8, 8, 8), np.uint16)
+    with pytest.raises(bsgpu.BsError):
+        ctx.pcm_pair(a, a, ctx.pcm_params(peaks_to_check=0))
+    with pytest.raises(bsgpu.BsError):
+        ctx.pcm_pair(a, a, ctx.pcm_params(peaks_to_check=1000))
