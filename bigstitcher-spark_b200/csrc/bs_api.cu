@@ -106,7 +106,10 @@ void bs_destroy(bs_ctx* ctx) {
     for (auto& kv : ctx->vols)
         if (kv.second.owned && kv.second.dev) cudaFree(kv.second.dev);
     bs_pcm_workspace_free(ctx);
-    if (ctx->fuse_views_dev) cudaFree(ctx->fuse_views_dev);
+    if (ctx->fuse_ring_dev) cudaFree(ctx->fuse_ring_dev);
+    if (ctx->fuse_ring_host) cudaFreeHost(ctx->fuse_ring_host);
+    for (int i = 0; i < bs_ctx::kFuseSlots; ++i)
+        if (ctx->fuse_slot_ev[i]) cudaEventDestroy(ctx->fuse_slot_ev[i]);
     if (ctx->fuse_out) cudaFree(ctx->fuse_out);
     cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);

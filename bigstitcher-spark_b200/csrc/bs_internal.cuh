@@ -57,8 +57,15 @@ struct bs_ctx {
     std::map<std::string, bs_prof_entry> prof_entries;
     std::vector<bs_pending_event> prof_pending;
     bs_pcm_workspace ws;
-    void* fuse_views_dev = nullptr;   // device copy of view descriptors
-    size_t fuse_views_cap = 0;
+    // ring of descriptor slots (pinned host mirror + device copy): a fusion call never has to
+    // synchronise the stream just to hand its view list to the kernel
+    static constexpr int kFuseSlots = 16;
+    void* fuse_ring_host = nullptr;
+    void* fuse_ring_dev = nullptr;
+    size_t fuse_slot_bytes = 0;
+    int fuse_next_slot = 0;
+    cudaEvent_t fuse_slot_ev[kFuseSlots] = {};
+    bool fuse_slot_used[kFuseSlots] = {};
     void* fuse_out = nullptr;         // device staging for host outputs
     size_t fuse_out_cap = 0;
     int sm_count = 148;

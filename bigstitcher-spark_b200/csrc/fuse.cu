@@ -283,6 +283,8 @@ static size_t out_elem_size(int dt) { return dt == BS_DTYPE_F32 ? 4 : dt == BS_D
 struct FusePrepared {
     FuseArgs args;
     int nviews;
+    int slot;
+    const FuseViewDev* views_dev;
 };
 
 // validate + upload view descriptors (and the cosine table); fills args except out pointers
@@ -331,28 +333,47 @@ static int fuse_prepare(bs_ctx* ctx, const bs_view* views, int n_views, const lo
             d.range[k] = views[i].blend_range[k];
         }
     }
-    size_t lut_bytes = (size_t)(FUSE_MAX_LUT + 2) * sizeof(float);
-    size_t need = lut_bytes + hv.size() * sizeof(FuseViewDev);
-    int rc = bs_ensure_dev(ctx, &ctx->fuse_views_dev, &ctx->fuse_views_cap, need > 4096 ? need : 4096);
-    if (rc) return rc;
-    // staging must outlive the async copy: use a synchronous copy of this small buffer
-    std::vector<unsigned char> stage(need);
-    float* lut = (float*)stage.data();
+    const size_t lut_bytes = (size_t)(FUSE_MAX_LUT + 2) * sizeof(float);
+    const size_t need = lut_bytes + hv.size() * sizeof(FuseViewDev);
+    if (need > ctx->fuse_slot_bytes) {
+        size_t sb = 1 << 16;
+        while (sb < need) sb <<= 1;
+        BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->fuse_ring_dev) cudaFree(ctx->fuse_ring_dev);
+        if (ctx->fuse_ring_host) cudaFreeHost(ctx->fuse_ring_host);
+        ctx->fuse_ring_dev = ctx->fuse_ring_host = nullptr;
+        ctx->fuse_slot_bytes = 0;
+        BS_CUDA(ctx, cudaMalloc(&ctx->fuse_ring_dev, sb * bs_ctx::kFuseSlots));
+        BS_CUDA(ctx, cudaHostAlloc(&ctx->fuse_ring_host, sb * bs_ctx::kFuseSlots, cudaHostAllocDefault));
+        for (int i = 0; i < bs_ctx::kFuseSlots; ++i) {
+            ctx->fuse_slot_used[i] = false;
+            if (!ctx->fuse_slot_ev[i])
+                BS_CUDA(ctx, cudaEventCreateWithFlags(&ctx->fuse_slot_ev[i], cudaEventDisableTiming));
+        }
+        ctx->fuse_slot_bytes = sb;
+    }
+    const int slot = ctx->fuse_next_slot;
+    ctx->fuse_next_slot = (slot + 1) % bs_ctx::kFuseSlots;
+    if (ctx->fuse_slot_used[slot]) BS_CUDA(ctx, cudaEventSynchronize(ctx->fuse_slot_ev[slot]));
+    unsigned char* hslot = (unsigned char*)ctx->fuse_ring_host + (size_t)slot * ctx->fuse_slot_bytes;
+    unsigned char* dslot = (unsigned char*)ctx->fuse_ring_dev + (size_t)slot * ctx->fuse_slot_bytes;
+    float* lut = (float*)hslot;
     const int n = p->blend_lut_n;
     if (n > 0) {
         for (int i = 0; i <= n; ++i) lut[i] = (float)((std::cos((1.0 - (double)i / n) * M_PI) + 1.0) / 2.0);
         lut[n + 1] = lut[n];
     }
-    if (!hv.empty()) memcpy(stage.data() + lut_bytes, hv.data(), hv.size() * sizeof(FuseViewDev));
-    BS_CUDA(ctx, cudaMemcpyAsync(ctx->fuse_views_dev, stage.data(), need, cudaMemcpyHostToDevice, ctx->stream));
-    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!hv.empty()) memcpy(hslot + lut_bytes, hv.data(), hv.size() * sizeof(FuseViewDev));
+    BS_CUDA(ctx, cudaMemcpyAsync(dslot, hslot, need, cudaMemcpyHostToDevice, ctx->stream));
+    prep->slot = slot;
+    prep->views_dev = (const FuseViewDev*)(dslot + lut_bytes);
 
     FuseArgs& a = prep->args;
     memset(&a, 0, sizeof(a));
     for (int d = 0; d < 3; ++d) { a.bmin[d] = block_min[d]; a.size[d] = (int)block_size[d]; }
     a.fusion_type = p->fusion_type;
     a.lut_n = n;
-    a.lut = (const float*)ctx->fuse_views_dev;
+    a.lut = (const float*)dslot;
     a.ctop = p->out_dtype == BS_DTYPE_U8 ? 255.0 : 65535.0;
     a.cmin = p->min_intensity;
     a.cscale = p->out_dtype == BS_DTYPE_F32 ? 1.0 : a.ctop / (p->max_intensity - p->min_intensity);
@@ -375,8 +396,7 @@ static int fuse_launch(bs_ctx* ctx, const FusePrepared& prep, const bs_fuse_para
               (a.size[2] + FUSE_ZT - 1) / FUSE_ZT);
     if (grid.y > 65535 || grid.z > 65535)
         return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: block too large for one launch (y/z tiles > 65535)");
-    const FuseViewDev* v =
-        (const FuseViewDev*)((const unsigned char*)ctx->fuse_views_dev + (size_t)(FUSE_MAX_LUT + 2) * sizeof(float));
+    const FuseViewDev* v = prep.views_dev;
     const bool winner = p->fusion_type >= BS_FUSE_MAX_INTENSITY;
     const bool lin = p->interpolation == 1;
     {
@@ -393,6 +413,8 @@ static int fuse_launch(bs_ctx* ctx, const FusePrepared& prep, const bs_fuse_para
         }
     }
     BS_CUDA(ctx, cudaGetLastError());
+    BS_CUDA(ctx, cudaEventRecord(ctx->fuse_slot_ev[prep.slot], ctx->stream));
+    ctx->fuse_slot_used[prep.slot] = true;
     return BS_OK;
 }
 

@@ -930,6 +930,7 @@ static int pcm_run(bs_ctx* ctx, const void* d1, const void* d2, const long long 
                 npx *= pc.sz[d];
             }
             if (overlap && npx >= min_px) {
+                out->pearson_px += npx;
                 c.npx = npx;
                 c.slot = nslots;
                 hc[nslots++] = pc;

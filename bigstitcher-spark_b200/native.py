@@ -44,7 +44,8 @@ class PcmParams(C.Structure):
 class PcmResultC(C.Structure):
     _fields_ = [("found", C.c_int), ("shift_int", C.c_longlong * 3), ("shift_sub", C.c_double * 3),
                 ("r", C.c_double), ("n_overlap_px", C.c_longlong), ("peak_index", C.c_longlong * 3),
-                ("pcm_value", C.c_double), ("pad", C.c_int * 3), ("n_candidates", C.c_int)]
+                ("pcm_value", C.c_double), ("pad", C.c_int * 3), ("n_candidates", C.c_int),
+                ("pearson_px", C.c_longlong)]
 
 
 class ViewC(C.Structure):
@@ -69,6 +70,7 @@ class PcmResult:
     pcm_value: float
     pad: tuple
     n_candidates: int
+    pearson_px: int = 0
 
 
 _lib = None
@@ -224,7 +226,7 @@ class Context:
     @staticmethod
     def _result(r: PcmResultC) -> PcmResult:
         return PcmResult(bool(r.found), tuple(r.shift_int), tuple(r.shift_sub), r.r, r.n_overlap_px,
-                         tuple(r.peak_index), r.pcm_value, tuple(r.pad), r.n_candidates)
+                         tuple(r.peak_index), r.pcm_value, tuple(r.pad), r.n_candidates, r.pearson_px)
 
     def pcm_pair(self, img1, img2, params: PcmParams | None = None, dims_xyz=None, dtype=None) -> PcmResult:
         """Phase correlation of one equal-size crop pair ([z,y,x] arrays, host or device)."""

@@ -96,6 +96,7 @@ typedef struct {
     double    pcm_value;        /* PCM value of that peak */
     int       pad[3];           /* padded FFT size used */
     int       n_candidates;     /* Pearson-verified candidates (>= min overlap) */
+    long long pearson_px;       /* sum of their overlap voxel counts (byte accounting) */
 } bs_pcm_result;
 
 void bs_pcm_default_params(bs_pcm_params* p);
