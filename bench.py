@@ -495,7 +495,7 @@ def main():
     ap.add_argument("--fusion-tile", type=int, default=576)
     ap.add_argument("--fusion-stride", type=int, default=491)
     ap.add_argument("--fusion-size", type=int, default=2048)
-    ap.add_argument("--fusion-distinct", type=int, default=4)
+    ap.add_argument("--fusion-distinct", type=int, default=64)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
