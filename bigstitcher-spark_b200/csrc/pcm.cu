@@ -39,7 +39,8 @@ struct XR2CArgs {
     int dtype;
     int dx, dy, dz;
     int Px, Py, Pz, M, pitch;
-    int Ey, Ez;
+    int ex;        // offset of the crop inside the padded x axis (= min(extension, dx))
+    int Ex, Ey, Ez;
     const int* idx_x; const float* w_x;
     const int* idx_y; const float* w_y;
     const int* idx_z; const float* w_z;
@@ -54,56 +55,114 @@ __device__ __forceinline__ float load_voxel(const void* p, int dtype, size_t i) 
     return (float)__ldg((const unsigned char*)p + i);
 }
 
+// One warp owns a line at a time: the row's y/z profile is warp-uniform, interior samples are
+// read as aligned ushort2 pairs, and each lane keeps XR_UNROLL independent loads in flight.
+#define XR_UNROLL 5
+template <class F>
 __global__ void __launch_bounds__(PCM_THREADS) k_fft_x_r2c(const __grid_constant__ XR2CArgs a) {
-    const int LB = 1 << a.lshift, ls = LB + 1;
+    const int M = F::kStatic ? F::N : a.M;
+    const int lshift = F::kStatic ? F::LSHIFT : a.lshift;
+    const int LB = 1 << lshift, ls = LB + 1;
+    const int Px = 2 * M;
+    const int pitch = F::kStatic ? ((F::N + 1 + 15) / 16) * 16 : a.pitch;
     float2* tw = bs_sm;
-    float2* b0 = bs_sm + a.Px;
-    float2* b1 = b0 + a.M * ls;
+    float2* b0 = bs_sm + Px;
+    float2* b1 = b0 + M * ls;
     const int zp = blockIdx.y, y0 = blockIdx.x * LB, im = blockIdx.z;
     float2* __restrict__ spec = a.spec[im];
-    const size_t rowbase = ((size_t)zp * a.Py + y0) * a.pitch;
+    const size_t rowbase = ((size_t)zp * a.Py + y0) * pitch;
     const int nlines = min(LB, a.Py - y0);
     if (zp >= a.Ez || y0 >= a.Ey) {  // every line of this CTA lies in the zero padding
-        const float2 z2 = make_float2(0.f, 0.f);
-        for (int i = threadIdx.x; i < nlines * a.pitch; i += blockDim.x) spec[rowbase + i] = z2;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4* d4 = reinterpret_cast<float4*>(spec + rowbase);
+        for (int i = threadIdx.x; i < nlines * (pitch >> 1); i += blockDim.x) d4[i] = z4;
         return;
     }
-    for (int i = threadIdx.x; i < a.Px; i += blockDim.x) tw[i] = a.tw[i];
+    for (int i = threadIdx.x; i < Px; i += blockDim.x) tw[i] = a.tw[i];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = PCM_THREADS / 32;
     const float wz = a.w_z[zp];
     const int sz = a.idx_z[zp];
     const void* img = a.img[im];
-    for (int item = threadIdx.x; item < LB * a.M; item += blockDim.x) {
-        const int l = item / a.M, n = item - l * a.M;
-        float2 v = make_float2(0.f, 0.f);
-        const int yp = y0 + l;
-        if (l < nlines && yp < a.Ey) {
-            const float wy = a.w_y[yp];
-            const size_t rb = ((size_t)sz * a.dy + a.idx_y[yp]) * a.dx;
-            const int xp = 2 * n;
-            const float g0 = (a.w_x[xp] * wy) * wz, g1 = (a.w_x[xp + 1] * wy) * wz;
-            if (g0 != 0.f) v.x = load_voxel(img, a.dtype, rb + a.idx_x[xp]) * g0;
-            if (g1 != 0.f) v.y = load_voxel(img, a.dtype, rb + a.idx_x[xp + 1]) * g1;
+    const int e0 = a.ex;
+    const bool vec_ok = a.dtype == BS_DTYPE_U16 && !(e0 & 1) && !(a.dx & 1) && !((size_t)img & 3);
+    // two lines per warp pass -> 2 * XR_UNROLL independent loads in flight per lane
+    for (int lA = wid; lA < LB; lA += 2 * NW) {
+        bool live[2];
+        float gyz[2], wy[2];
+        size_t rb[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int l = lA + h * NW, yp = y0 + l;
+            live[h] = l < LB && l < nlines && yp < a.Ey;
+            wy[h] = 0.f;
+            rb[h] = 0;
+            if (live[h]) {
+                wy[h] = a.w_y[yp];
+                rb[h] = ((size_t)sz * a.dy + a.idx_y[yp]) * a.dx;
+            }
+            gyz[h] = wy[h] * wz;  // == (1 * wy) * wz for interior samples
         }
-        b0[n * ls + l] = v;
+        for (int n0 = 0; n0 < M; n0 += 32 * XR_UNROLL) {
+            float2 v[2][XR_UNROLL];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int u = 0; u < XR_UNROLL; ++u) {
+                    const int n = n0 + u * 32 + lane;
+                    v[h][u] = make_float2(0.f, 0.f);
+                    if (live[h] && n < M) {
+                        const int xp = 2 * n;
+                        if (xp >= e0 && xp + 1 < e0 + a.dx) {
+                            if (vec_ok) {
+                                const ushort2 t = __ldg(reinterpret_cast<const ushort2*>(
+                                    (const unsigned short*)img + rb[h] + (xp - e0)));
+                                v[h][u] = make_float2((float)t.x * gyz[h], (float)t.y * gyz[h]);
+                            } else {
+                                v[h][u] = make_float2(load_voxel(img, a.dtype, rb[h] + (xp - e0)) * gyz[h],
+                                                      load_voxel(img, a.dtype, rb[h] + (xp - e0) + 1) * gyz[h]);
+                            }
+                        } else if (xp < a.Ex) {  // blended mirrored margin (a few samples per line)
+                            const float g0 = (a.w_x[xp] * wy[h]) * wz, g1 = (a.w_x[xp + 1] * wy[h]) * wz;
+                            if (g0 != 0.f) v[h][u].x = load_voxel(img, a.dtype, rb[h] + a.idx_x[xp]) * g0;
+                            if (g1 != 0.f) v[h][u].y = load_voxel(img, a.dtype, rb[h] + a.idx_x[xp + 1]) * g1;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int l = lA + h * NW;
+                if (l < LB) {
+#pragma unroll
+                    for (int u = 0; u < XR_UNROLL; ++u) {
+                        const int n = n0 + u * 32 + lane;
+                        if (n < M) b0[n * ls + l] = v[h][u];
+                    }
+                }
+            }
+        }
     }
     __syncthreads();
-    const float2* res = fft_tile(b0, b1, tw, a.plan, a.lshift, ls, 2);
+    const float2* res = F::run(b0, b1, tw, a.plan, lshift, ls, 2);
     // untangle the packed half-length transform into the real-input spectrum X[0..M]
-    for (int item = threadIdx.x; item < nlines * a.pitch; item += blockDim.x) {
-        const int l = item / a.pitch, k = item - l * a.pitch;
-        float2 X = make_float2(0.f, 0.f);
-        if (k <= a.M) {
-            const int k0 = (k == a.M) ? 0 : k;
-            const int k1 = (k == 0 || k == a.M) ? 0 : a.M - k;
-            const float2 Zk = res[k0 * ls + l];
-            float2 Zm = res[k1 * ls + l];
-            Zm.y = -Zm.y;
-            const float2 E = make_float2(0.5f * (Zk.x + Zm.x), 0.5f * (Zk.y + Zm.y));
-            const float2 D = make_float2(0.5f * (Zk.x - Zm.x), 0.5f * (Zk.y - Zm.y));
-            const float2 wD = cmulf(tw[k], D);
-            X = make_float2(E.x + wD.y, E.y - wD.x);  // E - i*w*D
+    for (int l = wid; l < nlines; l += NW) {
+        float2* srow = spec + rowbase + (size_t)l * pitch;
+        for (int k = lane; k < pitch; k += 32) {
+            float2 X = make_float2(0.f, 0.f);
+            if (k <= M) {
+                const int k0 = (k == M) ? 0 : k;
+                const int k1 = (k == 0 || k == M) ? 0 : M - k;
+                const float2 Zk = res[k0 * ls + l];
+                float2 Zm = res[k1 * ls + l];
+                Zm.y = -Zm.y;
+                const float2 E = make_float2(0.5f * (Zk.x + Zm.x), 0.5f * (Zk.y + Zm.y));
+                const float2 D = make_float2(0.5f * (Zk.x - Zm.x), 0.5f * (Zk.y - Zm.y));
+                const float2 wD = cmulf(tw[k], D);
+                X = make_float2(E.x + wD.y, E.y - wD.x);  // E - i*w*D
+            }
+            __stcg(srow + k, X);
         }
-        spec[rowbase + (size_t)l * a.pitch + k] = X;
     }
 }
 
@@ -121,15 +180,24 @@ struct StridedArgs {
     float thresh;        // normalisation threshold
 };
 
+template <int UNR>
 __device__ __forceinline__ void tile_load(float2* dst, const float2* g, long long estride, int N, int tshift) {
     const int vshift = tshift - 1;           // float4 vectors per row = TW/2
     const int vmask = (1 << vshift) - 1;
     const int nvec = N << vshift;
     float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll 4
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int e = i >> vshift, c = i & vmask;
-        d4[i] = __ldcg(reinterpret_cast<const float4*>(g + (long long)e * estride) + c);
+    for (int i0 = threadIdx.x; i0 < nvec; i0 += blockDim.x * UNR) {
+        float4 v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < nvec) v[u] = __ldcg(reinterpret_cast<const float4*>(g + (long long)(i >> vshift) * estride) + (i & vmask));
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < nvec) d4[i] = v[u];
+        }
     }
 }
 
@@ -139,20 +207,21 @@ __device__ __forceinline__ void tile_store(float2* g, const float2* src, long lo
     const int nvec = N << vshift;
     const float4* s4 = reinterpret_cast<const float4*>(src);
 #pragma unroll 4
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-        const int e = i >> vshift, c = i & vmask;
-        __stcg(reinterpret_cast<float4*>(g + (long long)e * estride) + c, s4[i]);
-    }
+    for (int i = threadIdx.x; i < nvec; i += blockDim.x)
+        __stcg(reinterpret_cast<float4*>(g + (long long)(i >> vshift) * estride) + (i & vmask), s4[i]);
 }
 
 __device__ __forceinline__ float2 unit_or_zero(float2 x, float thresh) {
-    const float m = sqrtf(x.x * x.x + x.y * x.y);
+    const float m2 = x.x * x.x + x.y * x.y;
+    const float m = sqrtf(m2);
     if (m < thresh) return make_float2(0.f, 0.f);
     return make_float2(x.x / m, x.y / m);
 }
 
+template <class F>
 __global__ void __launch_bounds__(PCM_THREADS) k_fft_strided(const __grid_constant__ StridedArgs a) {
-    const int TW = 1 << a.tshift, N = a.plan.n;
+    const int tshift = F::kStatic ? F::LSHIFT : a.tshift;
+    const int TW = 1 << tshift, N = F::kStatic ? F::N : a.plan.n;
     const int twpad = (N + 1) & ~1;
     float2* tw = bs_sm;
     float2* B0 = bs_sm + twpad;
@@ -161,18 +230,18 @@ __global__ void __launch_bounds__(PCM_THREADS) k_fft_strided(const __grid_consta
     for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = a.tw[i];
     if (a.mode == 0) {
         float2* g = (blockIdx.z ? a.b : a.a) + base;
-        tile_load(B0, g, a.estride, N, a.tshift);
+        tile_load<9>(B0, g, a.estride, N, tshift);
         __syncthreads();
-        const float2* res = fft_tile(B0, B1, tw, a.plan, a.tshift, TW, 1);
-        tile_store(g, res, a.estride, N, a.tshift);
+        const float2* res = F::run(B0, B1, tw, a.plan, tshift, TW, 1);
+        tile_store(g, res, a.estride, N, tshift);
     } else {
         float2* B2 = B1 + (size_t)N * TW;
-        tile_load(B0, a.a + base, a.estride, N, a.tshift);
-        tile_load(B1, a.b + base, a.estride, N, a.tshift);
+        tile_load<9>(B0, a.a + base, a.estride, N, tshift);
+        tile_load<9>(B1, a.b + base, a.estride, N, tshift);
         __syncthreads();
-        float2* rA = fft_tile(B0, B2, tw, a.plan, a.tshift, TW, 1);
+        float2* rA = F::run(B0, B2, tw, a.plan, tshift, TW, 1);
         float2* freeA = (rA == B0) ? B2 : B0;
-        float2* rB = fft_tile(B1, freeA, tw, a.plan, a.tshift, TW, 1);
+        float2* rB = F::run(B1, freeA, tw, a.plan, tshift, TW, 1);
         float2* free2 = (rB == B1) ? freeA : B1;
         const int tot = N * TW;
         for (int i = threadIdx.x; i < tot; i += blockDim.x) {
@@ -181,8 +250,8 @@ __global__ void __launch_bounds__(PCM_THREADS) k_fft_strided(const __grid_consta
             rA[i] = make_float2(x.x * y.x + x.y * y.y, x.x * y.y - x.y * y.x);  // conj(x) * y
         }
         __syncthreads();
-        const float2* rQ = fft_tile(rA, free2, tw, a.plan, a.tshift, TW, 1);
-        tile_store(a.a + base, rQ, a.estride, N, a.tshift);
+        const float2* rQ = F::run(rA, free2, tw, a.plan, tshift, TW, 1);
+        tile_store(a.a + base, rQ, a.estride, N, tshift);
     }
 }
 
@@ -197,30 +266,45 @@ struct XC2RArgs {
     float scale;
 };
 
+template <class F>
 __global__ void __launch_bounds__(PCM_THREADS) k_fft_x_c2r(const __grid_constant__ XC2RArgs a) {
-    const int LB = 1 << a.lshift, ls = LB + 1;
+    const int M = F::kStatic ? F::N : a.M;
+    const int lshift = F::kStatic ? F::LSHIFT : a.lshift;
+    const int LB = 1 << lshift, ls = LB + 1;
+    const int Px = 2 * M;
+    const int pitch = F::kStatic ? ((F::N + 1 + 15) / 16) * 16 : a.pitch;
     float2* tw = bs_sm;
-    float2* T0 = bs_sm + a.Px;                 // (M+1) * ls
-    float2* T1 = T0 + (size_t)(a.M + 1) * ls;  // M * ls
+    float2* T0 = bs_sm + Px;                 // (M+1) * ls
+    float2* T1 = T0 + (size_t)(M + 1) * ls;  // M * ls
     const int zp = blockIdx.y, y0 = blockIdx.x * LB;
-    const size_t rowbase = ((size_t)zp * a.Py + y0) * a.pitch;
+    const size_t rowbase = ((size_t)zp * a.Py + y0) * pitch;
     const int nlines = min(LB, a.Py - y0);
-    for (int i = threadIdx.x; i < a.Px; i += blockDim.x) tw[i] = a.tw[i];
-    const int M1 = a.M + 1;
-    for (int item = threadIdx.x; item < LB * M1; item += blockDim.x) {
-        const int l = item / M1, k = item - l * M1;
-        float2 v = make_float2(0.f, 0.f);
-        if (l < nlines) {
-            v = __ldcg(a.spec + rowbase + (size_t)l * a.pitch + k);
-            v.y = -v.y;  // partial inverse along y,z = conj of the forward transforms of conj data
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = PCM_THREADS / 32;
+    for (int i = threadIdx.x; i < Px; i += blockDim.x) tw[i] = a.tw[i];
+    for (int l = wid; l < LB; l += NW) {
+        const float2* srow = a.spec + rowbase + (size_t)l * pitch;
+        for (int k0 = 0; k0 <= M; k0 += 32 * XR_UNROLL) {
+            float2 v[XR_UNROLL];
+#pragma unroll
+            for (int u = 0; u < XR_UNROLL; ++u) {
+                const int k = k0 + u * 32 + lane;
+                v[u] = make_float2(0.f, 0.f);
+                if (l < nlines && k <= M) v[u] = __ldcg(srow + k);
+            }
+#pragma unroll
+            for (int u = 0; u < XR_UNROLL; ++u) {
+                const int k = k0 + u * 32 + lane;
+                // partial inverse along y,z = conj of the forward transforms of conj data
+                if (k <= M) T0[k * ls + l] = make_float2(v[u].x, -v[u].y);
+            }
         }
-        T0[k * ls + l] = v;
     }
     __syncthreads();
-    for (int item = threadIdx.x; item < a.M * LB; item += blockDim.x) {
-        const int k = item >> a.lshift, l = item & (LB - 1);
+    for (int item = threadIdx.x; item < M * LB; item += blockDim.x) {
+        const int k = item >> lshift, l = item & (LB - 1);
         const float2 Xk = T0[k * ls + l];
-        float2 Xm = T0[(a.M - k) * ls + l];
+        float2 Xm = T0[(M - k) * ls + l];
         Xm.y = -Xm.y;
         const float2 E = make_float2(0.5f * (Xk.x + Xm.x), 0.5f * (Xk.y + Xm.y));
         const float2 D = make_float2(0.5f * (Xk.x - Xm.x), 0.5f * (Xk.y - Xm.y));
@@ -231,12 +315,13 @@ __global__ void __launch_bounds__(PCM_THREADS) k_fft_x_c2r(const __grid_constant
         T1[k * ls + l] = make_float2(E.x - O.y, -(E.y + O.x));
     }
     __syncthreads();
-    const float2* res = fft_tile(T1, T0, tw, a.plan, a.lshift, ls, 2);
-    for (int item = threadIdx.x; item < nlines * a.M; item += blockDim.x) {
-        const int l = item / a.M, n = item - l * a.M;
-        const float2 r = res[n * ls + l];
-        float2* row = a.spec + rowbase + (size_t)l * a.pitch;
-        __stcg(row + n, make_float2(r.x * a.scale, -r.y * a.scale));
+    const float2* res = F::run(T1, T0, tw, a.plan, lshift, ls, 2);
+    for (int l = wid; l < nlines; l += NW) {
+        float2* row = a.spec + rowbase + (size_t)l * pitch;
+        for (int n = lane; n < M; n += 32) {
+            const float2 r = res[n * ls + l];
+            __stcg(row + n, make_float2(r.x * a.scale, -r.y * a.scale));
+        }
     }
 }
 
@@ -251,7 +336,7 @@ struct PeakEntry {
 struct PeakArgs {
     const float* pcm;
     int Px, Py, Pz;
-    long long rowpitch;  // floats
+    long long rowpitch;  // floats (multiple of 4, >= Px rounded up to 4)
     int K;
     PeakEntry* out;      // gridDim.x * K
 };
@@ -260,76 +345,111 @@ __device__ __forceinline__ bool peak_better(float v, long long i, float v2, long
     return v > v2 || (v == v2 && i < i2);
 }
 
+// A warp streams one row at a time with PK_UNROLL float4 loads in flight per lane.  The warp
+// keeps ONE sorted top-K list in registers (lane i holds the i-th best; K <= 32) and its K-th
+// value as a warp-uniform threshold, so after a few rows almost every voxel is rejected by a
+// single compare; only survivors fetch their six periodic neighbours and are inserted with a
+// ballot + shuffle shift.  Per-CTA merge of the 8 warp lists, then K entries per CTA go out.
+#define PK_UNROLL 5
+
+struct WarpTopK {
+    float v;        // lane i: value of the i-th best (or -inf)
+    long long i;    // its linear index (or LLONG_MAX)
+    float thr;      // warp-uniform: value of the K-th best (-inf until the list is full)
+};
+
+__device__ __forceinline__ void warp_topk_insert(WarpTopK& t, int K, float nv, long long ni, int lane) {
+    // rank of the new entry = number of current entries that are better
+    const bool mine_better = peak_better(t.v, t.i, nv, ni);
+    const unsigned better = __ballot_sync(0xffffffffu, mine_better && lane < K);
+    const int pos = __popc(better);
+    if (pos >= K) return;  // warp-uniform
+    const float upv = __shfl_up_sync(0xffffffffu, t.v, 1);
+    const long long upi = __shfl_up_sync(0xffffffffu, t.i, 1);
+    if (lane == pos) { t.v = nv; t.i = ni; }
+    else if (lane > pos && lane < K) { t.v = upv; t.i = upi; }
+    t.thr = __shfl_sync(0xffffffffu, t.v, K - 1);
+}
+
 __global__ void __launch_bounds__(PCM_THREADS) k_peaks(const __grid_constant__ PeakArgs a) {
-    float vals[PCM_KMAX];
-    long long idxs[PCM_KMAX];
-    int cnt = 0;
-    float thr = -INFINITY;  // K-th best of this thread once its list is full
     const int K = a.K;
     const long long nrows = (long long)a.Py * a.Pz;
-    for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
-        const int z = (int)(row / a.Py), y = (int)(row - (long long)z * a.Py);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = PCM_THREADS / 32;
+    const int nvec = (a.Px + 3) >> 2;
+    WarpTopK top;
+    top.v = -INFINITY;
+    top.i = 0x7fffffffffffffffLL;
+    top.thr = -INFINITY;
+    for (long long row = (long long)blockIdx.x * NW + wid; row < nrows; row += (long long)gridDim.x * NW) {
         const float* rp = a.pcm + row * a.rowpitch;
-        const float* rym = a.pcm + ((long long)z * a.Py + (y == 0 ? a.Py - 1 : y - 1)) * a.rowpitch;
-        const float* ryp = a.pcm + ((long long)z * a.Py + (y == a.Py - 1 ? 0 : y + 1)) * a.rowpitch;
-        const float* rzm = a.pcm + ((long long)(z == 0 ? a.Pz - 1 : z - 1) * a.Py + y) * a.rowpitch;
-        const float* rzp = a.pcm + ((long long)(z == a.Pz - 1 ? 0 : z + 1) * a.Py + y) * a.rowpitch;
-        for (int x = threadIdx.x; x < a.Px; x += blockDim.x) {
-            const float v = rp[x];
-            if (!(v > thr)) continue;  // later index loses ties; also drops NaN
-            if (v < rp[x == 0 ? a.Px - 1 : x - 1] || v < rp[x == a.Px - 1 ? 0 : x + 1]) continue;
-            if (v < rym[x] || v < ryp[x] || v < rzm[x] || v < rzp[x]) continue;
-            const long long li = row * a.Px + x;
-            int pos = cnt < K ? cnt : K - 1;
-            while (pos > 0 && vals[pos - 1] < v) {
-                vals[pos] = vals[pos - 1];
-                idxs[pos] = idxs[pos - 1];
-                --pos;
+        const float4* rp4 = reinterpret_cast<const float4*>(rp);
+        const int z = (int)(row / a.Py), y = (int)(row - (long long)z * a.Py);
+        for (int v0 = 0; v0 < nvec; v0 += 32 * PK_UNROLL) {
+            float4 q[PK_UNROLL];
+#pragma unroll
+            for (int u = 0; u < PK_UNROLL; ++u) {
+                const int vi = v0 + u * 32 + lane;
+                q[u] = vi < nvec ? __ldcs(rp4 + vi) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
             }
-            vals[pos] = v;
-            idxs[pos] = li;
-            if (cnt < K) ++cnt;
-            if (cnt == K) thr = vals[K - 1];
+#pragma unroll
+            for (int u = 0; u < PK_UNROLL; ++u) {
+                const int vi = v0 + u * 32 + lane;
+                const float c4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float v = c4[c];
+                    const int x = 4 * vi + c;
+                    bool cand = v >= top.thr && v > -INFINITY && x < a.Px;  // NaN fails both compares
+                    if (!__any_sync(0xffffffffu, cand)) continue;
+                    if (cand) {
+                        cand = !(v < rp[x == 0 ? a.Px - 1 : x - 1] || v < rp[x == a.Px - 1 ? 0 : x + 1]);
+                        if (cand) {
+                            const float* rym = a.pcm + ((long long)z * a.Py + (y == 0 ? a.Py - 1 : y - 1)) * a.rowpitch;
+                            const float* ryp = a.pcm + ((long long)z * a.Py + (y == a.Py - 1 ? 0 : y + 1)) * a.rowpitch;
+                            const float* rzm = a.pcm + ((long long)(z == 0 ? a.Pz - 1 : z - 1) * a.Py + y) * a.rowpitch;
+                            const float* rzp = a.pcm + ((long long)(z == a.Pz - 1 ? 0 : z + 1) * a.Py + y) * a.rowpitch;
+                            cand = !(v < rym[x] || v < ryp[x] || v < rzm[x] || v < rzp[x]);
+                        }
+                    }
+                    unsigned m = __ballot_sync(0xffffffffu, cand);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float nv = __shfl_sync(0xffffffffu, v, src);
+                        const int nx = __shfl_sync(0xffffffffu, x, src);
+                        warp_topk_insert(top, K, nv, row * a.Px + nx, lane);
+                    }
+                }
+            }
         }
     }
-    // K rounds of block arg-max over the heads of the per-thread sorted lists
-    __shared__ float s_v[PCM_THREADS / 32];
-    __shared__ long long s_i[PCM_THREADS / 32];
-    __shared__ int s_t[PCM_THREADS / 32];
-    __shared__ int s_win;
-    int head = 0;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int round = 0; round < K; ++round) {
-        float v = head < cnt ? vals[head] : -INFINITY;
-        long long li = head < cnt ? idxs[head] : 0x7fffffffffffffffLL;
-        int t = threadIdx.x;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const float v2 = __shfl_down_sync(0xffffffffu, v, off);
-            const long long i2 = __shfl_down_sync(0xffffffffu, li, off);
-            const int t2 = __shfl_down_sync(0xffffffffu, t, off);
-            if (peak_better(v2, i2, v, li)) { v = v2; li = i2; t = t2; }
-        }
-        if (lane == 0) { s_v[wid] = v; s_i[wid] = li; s_t[wid] = t; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            float bv = s_v[0];
-            long long bi = s_i[0];
-            int bt = s_t[0];
-            for (int w = 1; w < PCM_THREADS / 32; ++w)
-                if (peak_better(s_v[w], s_i[w], bv, bi)) { bv = s_v[w]; bi = s_i[w]; bt = s_t[w]; }
+    // merge the warp lists of this CTA into warp 0's list, then write K entries
+    __shared__ float s_v[NW * PCM_KMAX];
+    __shared__ long long s_i[NW * PCM_KMAX];
+    if (lane < K) { s_v[wid * PCM_KMAX + lane] = top.v; s_i[wid * PCM_KMAX + lane] = top.i; }
+    __syncthreads();
+    if (wid == 0) {
+        for (int w = 1; w < NW; ++w)
+            for (int e = 0; e < K; ++e) {
+                const float nv = s_v[w * PCM_KMAX + e];
+                if (nv == -INFINITY) break;  // lists are sorted; uniform across the warp
+                warp_topk_insert(top, K, nv, s_i[w * PCM_KMAX + e], lane);
+            }
+        if (lane < K) {
             PeakEntry e;
-            e.val = bv;
+            e.val = top.v;
             e.pad = 0;
-            e.idx = (bv == -INFINITY) ? -1 : bi;
-            a.out[(size_t)blockIdx.x * K + round] = e;
-            s_win = (bv == -INFINITY) ? -1 : bt;
+            e.idx = (top.v == -INFINITY) ? -1 : top.i;
+            a.out[(size_t)blockIdx.x * K + lane] = e;
         }
-        __syncthreads();
-        if (s_win == (int)threadIdx.x) ++head;
-        __syncthreads();
     }
 }
+
+// compile-time specialisations: padded 512^3 overlaps -> 540^3 (x half-length 270)
+typedef FftStatic<270, 4, 17, 2, PCM_THREADS, 9, 6, 5> FftX270;
+typedef FftStatic<270, 3, 9, 2, PCM_THREADS, 9, 6, 5> FftX270L8;
+typedef FftStatic<540, 3, 8, 1, PCM_THREADS, 9, 10, 6> FftS540;
 
 struct GatherArgs {
     const float* pcm;
@@ -520,9 +640,11 @@ struct PcmGeometry {
     int d[3], ext[3], P[3], E[3];
     int M, pitch;
     FftPlan plan_x, plan_y, plan_z;
-    int lshift_x;   // log2 lines per CTA in the x kernels
+    int lshift_x;   // log2 lines per CTA in the c2r kernel
+    int lshift_r2c; // log2 lines per CTA in the r2c kernel (fewer lines -> more CTAs/SM to hide load latency)
     int tshift_y, tshift_z;
     size_t smem_x_r2c, smem_x_c2r, smem_y, smem_z;
+    bool static_x, static_y, static_z;  // compile-time specialised kernels apply
 };
 
 struct PcmDeviceTables {
@@ -592,6 +714,8 @@ static int pcm_geometry(bs_ctx* ctx, const long long dims[3], const int ext[3], 
         if (ls == 0) return bs_set_error(ctx, BS_ERR_UNSUPPORTED, "pcm: x size %d too large for shared memory", g->P[0]);
     }
     g->lshift_x = ls;
+    g->lshift_r2c = std::min(ls, env_int("BS_FFT_R2C_LINES_LOG2", 3));
+    g->smem_x_r2c = ((size_t)g->P[0] + 2 * (size_t)g->M * ((1 << g->lshift_r2c) + 1)) * sizeof(float2);
     auto strided = [&](int N, int nbuf, int pref, int* tshift, size_t* smem) -> bool {
         for (int ts = pref; ts >= 1; --ts) {
             const size_t b = ((size_t)((N + 1) & ~1) + (size_t)nbuf * N * (1 << ts)) * sizeof(float2);
@@ -602,6 +726,11 @@ static int pcm_geometry(bs_ctx* ctx, const long long dims[3], const int ext[3], 
     if (!strided(g->P[1], 2, env_int("BS_FFT_YTILE_LOG2", 3), &g->tshift_y, &g->smem_y) ||
         !strided(g->P[2], 3, env_int("BS_FFT_ZTILE_LOG2", 3), &g->tshift_z, &g->smem_z))
         return bs_set_error(ctx, BS_ERR_UNSUPPORTED, "pcm: y/z size %dx%d too large for shared memory", g->P[1], g->P[2]);
+    const bool allow_static = env_int("BS_FFT_STATIC", 1) != 0;
+    g->static_x = allow_static && g->M == FftX270::N && (g->lshift_x == FftX270::LSHIFT || g->lshift_x == FftX270L8::LSHIFT) &&
+                  (g->lshift_r2c == 3 || g->lshift_r2c == 4);
+    g->static_y = allow_static && g->P[1] == FftS540::N && g->tshift_y == FftS540::LSHIFT;
+    g->static_z = allow_static && g->P[2] == FftS540::N && g->tshift_z == FftS540::LSHIFT;
     return BS_OK;
 }
 
@@ -669,9 +798,14 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
                            PcmDeviceTables* t) {
     if (!ctx->pcm_attr_done) {
         int rc;
-        if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c, 0))) return rc;
-        if ((rc = set_smem(ctx, (const void*)k_fft_strided, 0))) return rc;
-        if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c<FftGeneric>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_strided<FftGeneric>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftGeneric>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c<FftX270>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c<FftX270L8>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftX270L8>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_strided<FftS540>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftX270>, 0))) return rc;
         ctx->pcm_attr_done = true;
     }
     bs_pcm_workspace& ws = ctx->ws;
@@ -684,17 +818,20 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         a.dtype = dtype;
         a.dx = g.d[0]; a.dy = g.d[1]; a.dz = g.d[2];
         a.Px = g.P[0]; a.Py = g.P[1]; a.Pz = g.P[2]; a.M = g.M; a.pitch = g.pitch;
-        a.Ey = g.E[1]; a.Ez = g.E[2];
+        a.ex = std::min(g.ext[0], g.d[0]);
+        a.Ex = g.E[0]; a.Ey = g.E[1]; a.Ez = g.E[2];
         a.idx_x = t->idx[0]; a.w_x = t->w[0];
         a.idx_y = t->idx[1]; a.w_y = t->w[1];
         a.idx_z = t->idx[2]; a.w_z = t->w[2];
         a.tw = t->tw[0];
         a.plan = g.plan_x;
-        a.lshift = g.lshift_x;
-        const int LB = 1 << g.lshift_x;
+        a.lshift = g.lshift_r2c;
+        const int LB = 1 << g.lshift_r2c;
         dim3 grid((g.P[1] + LB - 1) / LB, g.P[2], 2);
         bs_launch_scope sc(ctx, "fft_x_r2c");
-        k_fft_x_r2c<<<grid, PCM_THREADS, g.smem_x_r2c, ctx->stream>>>(a);
+        if (g.static_x && g.lshift_r2c == 3) k_fft_x_r2c<FftX270L8><<<grid, PCM_THREADS, g.smem_x_r2c, ctx->stream>>>(a);
+        else if (g.static_x && g.lshift_r2c == 4) k_fft_x_r2c<FftX270><<<grid, PCM_THREADS, g.smem_x_r2c, ctx->stream>>>(a);
+        else k_fft_x_r2c<FftGeneric><<<grid, PCM_THREADS, g.smem_x_r2c, ctx->stream>>>(a);
     }
     BS_CUDA(ctx, cudaGetLastError());
     {
@@ -709,7 +846,8 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         a.thresh = 0.f;
         dim3 grid(g.pitch >> g.tshift_y, g.P[2], 2);
         bs_launch_scope sc(ctx, "fft_y");
-        k_fft_strided<<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
+        if (g.static_y) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
+        else k_fft_strided<FftGeneric><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
     }
     BS_CUDA(ctx, cudaGetLastError());
     {
@@ -724,7 +862,8 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         a.thresh = 1e-5f;  // PhaseCorrelation2Util.normalizeInterval threshold
         dim3 grid(g.pitch >> g.tshift_z, g.P[1], 1);
         bs_launch_scope sc(ctx, "fft_z_xpower");
-        k_fft_strided<<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
+        if (g.static_z) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
+        else k_fft_strided<FftGeneric><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
     }
     BS_CUDA(ctx, cudaGetLastError());
     {
@@ -739,7 +878,8 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         a.thresh = 0.f;
         dim3 grid(g.pitch >> g.tshift_y, g.P[2], 1);
         bs_launch_scope sc(ctx, "fft_y_inv");
-        k_fft_strided<<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
+        if (g.static_y) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
+        else k_fft_strided<FftGeneric><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
     }
     BS_CUDA(ctx, cudaGetLastError());
     {
@@ -753,7 +893,9 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         const int LB = 1 << g.lshift_x;
         dim3 grid((g.P[1] + LB - 1) / LB, g.P[2], 1);
         bs_launch_scope sc(ctx, "fft_x_c2r");
-        k_fft_x_c2r<<<grid, PCM_THREADS, g.smem_x_c2r, ctx->stream>>>(a);
+        if (g.static_x && g.lshift_x == 3) k_fft_x_c2r<FftX270L8><<<grid, PCM_THREADS, g.smem_x_c2r, ctx->stream>>>(a);
+        else if (g.static_x) k_fft_x_c2r<FftX270><<<grid, PCM_THREADS, g.smem_x_c2r, ctx->stream>>>(a);
+        else k_fft_x_c2r<FftGeneric><<<grid, PCM_THREADS, g.smem_x_c2r, ctx->stream>>>(a);
     }
     BS_CUDA(ctx, cudaGetLastError());
     return BS_OK;
@@ -840,7 +982,7 @@ static int pcm_run(bs_ctx* ctx, const void* d1, const void* d2, const long long 
 
     bs_pcm_workspace& ws = ctx->ws;
     const int K = p->peaks_to_check;
-    const int peak_ctas = std::min(ctx->sm_count * 4, g.P[1] * g.P[2]);
+    const int peak_ctas = std::max(1, std::min(ctx->sm_count * 8, (g.P[1] * g.P[2] + 7) / 8));
     // small-buffer layout (device and pinned mirror share offsets)
     unsigned char* dsmall = (unsigned char*)ws.small;
     unsigned char* hsmall = (unsigned char*)ws.small_host;
