@@ -414,7 +414,7 @@ def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
     hosts = {}
     for i in mine:
         key = tiles[i].data_ptr()
-        if key not in hosts:
+        if key not in hosts and not args.skip_fusion_e2e:
             hosts[key] = tiles[i].cpu().pin_memory()
     hout = torch.empty(256 * 256 * 128, dtype=torch.float32).pin_memory()
     hout_np = hout.numpy()
@@ -437,10 +437,13 @@ def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
             ctx.volume_free(h)
 
     rev = {handles[i]: i for i in mine}
-    step_host()
-    e2e_ms, _ = timed(step_host, max(1, min(args.steps, 2)))
-    e2e_ms_step = e2e_ms / max(1, min(args.steps, 2))
-    e2e_value = nvox_total / (e2e_ms_step / 1000.0) / 1e6
+    if args.skip_fusion_e2e:
+        e2e_ms_step, e2e_value = float("nan"), float("nan")
+    else:
+        step_host()
+        e2e_ms, _ = timed(step_host, max(1, min(args.steps, 2)))
+        e2e_ms_step = e2e_ms / max(1, min(args.steps, 2))
+        e2e_value = nvox_total / (e2e_ms_step / 1000.0) / 1e6
     h2d = len(mine) * tile ** 3 * 2
     d2h = nvox_rank * 4
 
@@ -490,6 +493,8 @@ def main():
     ap.add_argument("--host-pairs", type=int, default=8)
     ap.add_argument("--skip-fusion", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-fusion-e2e", action="store_true")
+    ap.add_argument("--skip-pcm", action="store_true", help="debug: tiny PCM workload")
     ap.add_argument("--ref-full", action="store_true", help="reference arm: run all warm-up steps too")
     ap.add_argument("--fusion-grid", type=int, default=4)
     ap.add_argument("--fusion-tile", type=int, default=576)

@@ -16,7 +16,7 @@
 #define FUSE_TX 32
 #define FUSE_TY 8
 #define FUSE_ZT 8
-#define FUSE_CHUNK 256
+#define FUSE_CHUNK 64
 #define FUSE_MAX_LUT 256
 
 struct FuseViewDev {
@@ -40,6 +40,7 @@ struct FuseArgs {
     void* out;
     float* acc_wi;         // accumulate mode
     float* acc_w;
+    int no_stage;          // debug: force the global-gather path (env BS_FUSE_NO_STAGE)
 };
 
 template <typename T>
@@ -84,21 +85,126 @@ __device__ __forceinline__ float sample_any(const void* d, int dtype, int dx, in
     return sample<unsigned char, LINEAR>((const unsigned char*)d, dx, dy, dz, sx, sy, sz);
 }
 
-// cosine blending weight along one axis; returns false when the total weight is 0
-__device__ __forceinline__ bool blend_axis(float l, float dm1, float border, float range, int lut_n,
+// ---- staged footprint: a fixed FS_X x FS_Y x FS_Z float box per (CTA tile, view) in shared memory
+#define FS_X 40
+#define FS_Y 12
+#define FS_Z 12
+#define FS_N (FS_X * FS_Y * FS_Z)   // 5760 floats = 22.5 KB
+extern __shared__ float fuse_dyn_smem[];  // second stage buffer (content weights), sized at launch
+
+// Per (CTA tile, active view) constants, computed once in double by one thread and kept in
+// shared memory: everything the per-voxel loop needs is float and tile-relative.
+struct ViewTile {
+    float m[9];        // linear part of world->source
+    float o[3];        // source coordinate of the tile origin, relative to the box origin b0
+    int b0[3];         // box origin in source pixels (staged: clamped so the box stays inside the volume)
+    int dims[3];
+    float border[3];
+    float inv_range[3];
+    float range[3];
+    const void* data;
+    const float* content;
+    int dtype;
+    int staged;
+    int interior;      // every upper tap of the tile exists (no clamping at the volume's far faces)
+    int plateau;       // every voxel of the tile is >= blend range away from all faces: weight == 1
+    int vec4;          // staged rows can be read as aligned 8-byte ushort4 vectors
+};
+
+template <typename T>
+__device__ __forceinline__ void stage_fixed(float* __restrict__ st, const T* __restrict__ d, const ViewTile& t,
+                                            int tid) {
+    // FS_N elements, constant index math, every load independent of the others
+    const int dx = t.dims[0], dy = t.dims[1], dz = t.dims[2];
+#pragma unroll 6
+    for (int i = tid; i < FS_N; i += FUSE_TX * FUSE_TY) {
+        const int xx = i % FS_X, r = i / FS_X;
+        const int yy = r % FS_Y, zz = r / FS_Y;
+        const int gx = min(t.b0[0] + xx, dx - 1), gy = min(t.b0[1] + yy, dy - 1), gz = min(t.b0[2] + zz, dz - 1);
+        st[i] = (float)__ldg(d + ((size_t)gz * dy + gy) * dx + gx);
+    }
+}
+
+// uint16 fast path: box origin and row pitch are multiples of 4 voxels and the box lies inside the
+// volume along x -> 10 aligned 8-byte loads per row, 1440 per box (5.6 per thread, all independent)
+__device__ __forceinline__ void stage_fixed_u16x4(float* __restrict__ st, const unsigned short* __restrict__ d,
+                                                  const ViewTile& t, int tid) {
+    const int dx = t.dims[0], dy = t.dims[1], dz = t.dims[2];
+    constexpr int VPR = FS_X / 4;
+#pragma unroll 6
+    for (int i = tid; i < FS_N / 4; i += FUSE_TX * FUSE_TY) {
+        const int xv = i % VPR, r = i / VPR;
+        const int yy = r % FS_Y, zz = r / FS_Y;
+        const int gy = min(t.b0[1] + yy, dy - 1), gz = min(t.b0[2] + zz, dz - 1);
+        const uint2 q = __ldg(reinterpret_cast<const uint2*>(d + ((size_t)gz * dy + gy) * dx + t.b0[0]) + xv);
+        float4 f;
+        f.x = (float)(q.x & 0xffffu); f.y = (float)(q.x >> 16);
+        f.z = (float)(q.y & 0xffffu); f.w = (float)(q.y >> 16);
+        reinterpret_cast<float4*>(st)[i] = f;
+    }
+}
+
+__device__ __forceinline__ void stage_fixed_any(float* st, const void* d, int dtype, const ViewTile& t, int tid) {
+    if (dtype == BS_DTYPE_U16) {
+        if (t.vec4) stage_fixed_u16x4(st, (const unsigned short*)d, t, tid);
+        else stage_fixed(st, (const unsigned short*)d, t, tid);
+    } else if (dtype == BS_DTYPE_F32) stage_fixed(st, (const float*)d, t, tid);
+    else stage_fixed(st, (const unsigned char*)d, t, tid);
+}
+
+// n-linear sample from the staged box at box-relative coordinates (rx, ry, rz)
+template <bool INTERIOR>
+__device__ __forceinline__ float sample_staged(const float* __restrict__ st, const ViewTile& t, float rx, float ry,
+                                               float rz) {
+    const float fx = floorf(rx), fy = floorf(ry), fz = floorf(rz);
+    const float tx = rx - fx, ty = ry - fy, tz = rz - fz;
+    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const float* p = st + (z0 * FS_Y + y0) * FS_X + x0;
+    float a000, a001, a010, a011, a100, a101, a110, a111;
+    if (INTERIOR) {  // immediate offsets
+        a000 = p[0]; a001 = p[1]; a010 = p[FS_X]; a011 = p[FS_X + 1];
+        a100 = p[FS_X * FS_Y]; a101 = p[FS_X * FS_Y + 1]; a110 = p[FS_X * FS_Y + FS_X]; a111 = p[FS_X * FS_Y + FS_X + 1];
+    } else {
+        const int ox = (t.b0[0] + x0 + 1 < t.dims[0]) ? 1 : 0;
+        const int oy = (t.b0[1] + y0 + 1 < t.dims[1]) ? FS_X : 0;
+        const int oz = (t.b0[2] + z0 + 1 < t.dims[2]) ? FS_X * FS_Y : 0;
+        a000 = p[0]; a001 = p[ox]; a010 = p[oy]; a011 = p[oy + ox];
+        a100 = p[oz]; a101 = p[oz + ox]; a110 = p[oz + oy]; a111 = p[oz + oy + ox];
+    }
+    const float c00 = a000 + tx * (a001 - a000);
+    const float c01 = a010 + tx * (a011 - a010);
+    const float c10 = a100 + tx * (a101 - a100);
+    const float c11 = a110 + tx * (a111 - a110);
+    const float c0 = c00 + ty * (c01 - c00);
+    const float c1 = c10 + ty * (c11 - c10);
+    return c0 + tz * (c1 - c0);
+}
+
+// cosine blending weight along one axis (l = absolute source coordinate); false when weight is 0
+__device__ __forceinline__ bool blend_axis(float l, float dm1, float border, float inv_range, int lut_n,
                                            const float* s_lut, float& w) {
-    float dist = fmaxf(0.f, fminf(l - border, (dm1 - l) - border));
+    const float dist = fmaxf(0.f, fminf(l - border, (dm1 - l) - border));
     if (dist == 0.f) return false;
-    float rel = dist / range;
+    const float rel = dist * inv_range;
     if (rel < 1.f) {
         float f;
         if (lut_n > 0) {
-            float pos = rel * (float)lut_n;
-            int i = (int)pos;
-            float s = pos - (float)i;
+            const float pos = rel * (float)lut_n;
+            const int i = (int)pos;
+            const float s = pos - (float)i;
             f = s_lut[i] * (1.0f - s) + s_lut[i + 1] * s;
         } else {
-            f = 0.5f * (cospif(1.0f - rel) + 1.0f);
+            // (cos((1 - rel) pi) + 1) / 2 == sin^2(pi rel / 2): no cancellation for tiny weights.
+            // sin(pi y), y = rel / 2 in [0, 0.5): odd Taylor polynomial to y^11 (rel. error < 1e-7)
+            const float yh = 0.5f * rel, y2 = yh * yh;
+            float p = -0.0073704309f;              // -pi^11 / 11!
+            p = fmaf(p, y2, 0.0821458866f);         //  pi^9 / 9!
+            p = fmaf(p, y2, -0.5992645293f);        // -pi^7 / 7!
+            p = fmaf(p, y2, 2.5501640399f);         //  pi^5 / 5!
+            p = fmaf(p, y2, -5.1677127800f);        // -pi^3 / 3!
+            p = fmaf(p, y2, 3.1415926536f);         //  pi
+            const float sn = p * yh;
+            f = sn * sn;
         }
         w *= f;
     }
@@ -107,53 +213,64 @@ __device__ __forceinline__ bool blend_axis(float l, float dm1, float border, flo
 
 // KIND 0: weighted average family (AVG, AVG_BLEND, *_CONTENT); KIND 1: winner family.
 // ACCUM: add partial sums into acc_wi/acc_w instead of producing the final voxel.
+//
+// Per CTA tile (32 x 8 x FUSE_ZT output voxels) and per overlapping view, one thread derives
+// the tile-relative float transform in double; the source footprint of the tile (40 x 12 x 12
+// box starting at the footprint's lower corner) is copied once into shared memory as float
+// with independent, row-coalesced loads, and the 8 taps of every voxel then come from shared
+// memory.  Footprints that do not fit the box (down-scaling, strong rotation) and nearest-
+// neighbour sampling gather from global memory through L1/L2 instead.
 template <int KIND, bool LINEAR, int OUT, bool ACCUM>
-__global__ void __launch_bounds__(FUSE_TX* FUSE_TY)
+__global__ void __launch_bounds__(FUSE_TX* FUSE_TY, 3)
 fuse_kernel(const FuseViewDev* __restrict__ views, int nviews, FuseArgs a) {
     __shared__ int s_active[FUSE_CHUNK];
+    __shared__ ViewTile s_vt[FUSE_CHUNK];
     __shared__ int s_nactive;
     __shared__ float s_lut[FUSE_MAX_LUT + 2];
+    __shared__ __align__(16) float s_stage[FS_N];
+    float* s_stage_c = fuse_dyn_smem;
 
     const int tid = threadIdx.y * FUSE_TX + threadIdx.x;
+    constexpr int NT = FUSE_TX * FUSE_TY;
     const int x = blockIdx.x * FUSE_TX + threadIdx.x;
     const int y = blockIdx.y * FUSE_TY + threadIdx.y;
     const int z0 = blockIdx.z * FUSE_ZT;
     const bool valid = x < a.size[0] && y < a.size[1];
     const int ft = a.fusion_type;
     const bool use_blend = ft == BS_FUSE_AVG_BLEND || ft == BS_FUSE_AVG_BLEND_CONTENT || ft == BS_FUSE_CLOSEST_PIXEL_WINS;
-    const bool use_content = ft == BS_FUSE_AVG_CONTENT || ft == BS_FUSE_AVG_BLEND_CONTENT;
+    const bool use_content = KIND == 0 && (ft == BS_FUSE_AVG_CONTENT || ft == BS_FUSE_AVG_BLEND_CONTENT);
 
     if (a.lut_n > 0)
-        for (int i = tid; i < a.lut_n + 2; i += FUSE_TX * FUSE_TY) s_lut[i] = a.lut[i];
+        for (int i = tid; i < a.lut_n + 2; i += NT) s_lut[i] = a.lut[i];
 
     float acc0[FUSE_ZT];  // KIND0: sum w*I ; KIND1: best value
     float acc1[FUSE_ZT];  // KIND0: sum w   ; KIND1: best weight (CLOSEST) / have flag
 #pragma unroll
     for (int k = 0; k < FUSE_ZT; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
 
-    const double wx = (double)(a.bmin[0] + x);
-    const double wy = (double)(a.bmin[1] + y);
+    const float tx = (float)threadIdx.x, ty = (float)threadIdx.y;
+    const int nz = min(FUSE_ZT, a.size[2] - z0);
 
     for (int chunk = 0; chunk < nviews; chunk += FUSE_CHUNK) {
         __syncthreads();
         if (tid == 0) s_nactive = 0;
         __syncthreads();
-        // ---- cull: source AABB of the tile's 8 corners against [0, dim-1] (+-1e-3 guard)
-        for (int vi = chunk + tid; vi < min(nviews, chunk + FUSE_CHUNK); vi += FUSE_TX * FUSE_TY) {
+        // ---- cull: source AABB of the tile's corners against [0, dim-1] (+-1e-3 guard)
+        const double cx0 = (double)(a.bmin[0] + (long long)blockIdx.x * FUSE_TX);
+        const double cy0 = (double)(a.bmin[1] + (long long)blockIdx.y * FUSE_TY);
+        const double cz0 = (double)(a.bmin[2] + z0);
+        const double ex = (double)(min(FUSE_TX, a.size[0] - (int)blockIdx.x * FUSE_TX) - 1);
+        const double ey = (double)(min(FUSE_TY, a.size[1] - (int)blockIdx.y * FUSE_TY) - 1);
+        const double ez = (double)(nz - 1);
+        for (int vi = chunk + tid; vi < min(nviews, chunk + FUSE_CHUNK); vi += NT) {
             const FuseViewDev& v = views[vi];
-            double cx0 = (double)(a.bmin[0] + (long long)blockIdx.x * FUSE_TX);
-            double cy0 = (double)(a.bmin[1] + (long long)blockIdx.y * FUSE_TY);
-            double cz0 = (double)(a.bmin[2] + z0);
-            double cx1 = cx0 + (double)(min(FUSE_TX, a.size[0] - (int)blockIdx.x * FUSE_TX) - 1);
-            double cy1 = cy0 + (double)(min(FUSE_TY, a.size[1] - (int)blockIdx.y * FUSE_TY) - 1);
-            double cz1 = cz0 + (double)(min(FUSE_ZT, a.size[2] - z0) - 1);
             bool hit = true;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                double lo = v.inv[4 * r + 3], hi = lo;
-                double m0 = v.inv[4 * r], m1 = v.inv[4 * r + 1], m2 = v.inv[4 * r + 2];
-                lo += fmin(m0 * cx0, m0 * cx1) + fmin(m1 * cy0, m1 * cy1) + fmin(m2 * cz0, m2 * cz1);
-                hi += fmax(m0 * cx0, m0 * cx1) + fmax(m1 * cy0, m1 * cy1) + fmax(m2 * cz0, m2 * cz1);
+                const double m0 = v.inv[4 * r], m1 = v.inv[4 * r + 1], m2 = v.inv[4 * r + 2];
+                const double org = fma(m0, cx0, fma(m1, cy0, fma(m2, cz0, v.inv[4 * r + 3])));
+                const double lo = org + fmin(0.0, m0 * ex) + fmin(0.0, m1 * ey) + fmin(0.0, m2 * ez);
+                const double hi = org + fmax(0.0, m0 * ex) + fmax(0.0, m1 * ey) + fmax(0.0, m2 * ez);
                 if (hi < -1e-3 || lo > (double)(v.dims[r] - 1) + 1e-3) hit = false;
             }
             if (hit) s_active[atomicAdd(&s_nactive, 1)] = vi;
@@ -169,35 +286,87 @@ fuse_kernel(const FuseViewDev* __restrict__ views, int nviews, FuseArgs a) {
             }
         }
         __syncthreads();
-        if (!valid) continue;
+        // ---- per-view tile constants
+        for (int ai = tid; ai < nact; ai += NT) {
+            const FuseViewDev& v = views[s_active[ai]];
+            ViewTile& t = s_vt[ai];
+            bool fits = LINEAR && a.no_stage == 0;
+            bool interior = true, plateau = true;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const double m0 = v.inv[4 * r], m1 = v.inv[4 * r + 1], m2 = v.inv[4 * r + 2];
+                const double org = fma(m0, cx0, fma(m1, cy0, fma(m2, cz0, v.inv[4 * r + 3])));
+                const double lo = org + fmin(0.0, m0 * ex) + fmin(0.0, m1 * ey) + fmin(0.0, m2 * ez);
+                const double hi = org + fmax(0.0, m0 * ex) + fmax(0.0, m1 * ey) + fmax(0.0, m2 * ez);
+                // taps floor(s) .. floor(s)+1 of every in-range s; eps covers float rounding of s
+                const double eps = 2e-3 + 2e-7 * fmax(fabs(lo), fabs(hi));
+                const int f0 = max((int)floor(fmax(lo - eps, 0.0)), 0);
+                const int f1 = min((int)floor(fmin(hi + eps, (double)(v.dims[r] - 1))) + 1, v.dims[r] - 1);
+                const int cap = r == 0 ? FS_X : (r == 1 ? FS_Y : FS_Z);
+                int g0 = f0;
+                if (r == 0) g0 &= ~3;                      // 4-voxel aligned box origin along x (vector staging)
+                if (f1 - g0 + 1 > cap - 1) fits = false;   // one spare row/column: a tap at weight 0 may touch f1 + 1
+                if (f1 + 1 > v.dims[r] - 1) interior = false;
+                if (!(lo - eps - (double)v.border[r] >= (double)v.range[r] &&
+                      (double)(v.dims[r] - 1) - (hi + eps) - (double)v.border[r] >= (double)v.range[r])) plateau = false;
+                t.b0[r] = g0;
+                t.o[r] = (float)(org - (double)g0);
+                t.m[3 * r] = (float)m0; t.m[3 * r + 1] = (float)m1; t.m[3 * r + 2] = (float)m2;
+                t.dims[r] = v.dims[r];
+                t.border[r] = v.border[r];
+                t.range[r] = v.range[r];
+                t.inv_range[r] = 1.0f / v.range[r];
+            }
+            t.data = v.data;
+            t.content = v.content;
+            t.dtype = v.dtype;
+            t.staged = fits ? 1 : 0;
+            t.interior = interior ? 1 : 0;
+            t.plateau = plateau ? 1 : 0;
+            t.vec4 = (v.dtype == BS_DTYPE_U16 && (v.dims[0] & 3) == 0 && ((size_t)v.data & 7) == 0 &&
+                      t.b0[0] + FS_X <= v.dims[0]) ? 1 : 0;
+        }
+        __syncthreads();
 
         for (int ai = 0; ai < nact; ++ai) {
-            const FuseViewDev& v = views[s_active[ai]];
-            const double m02 = v.inv[2], m12 = v.inv[6], m22 = v.inv[10];
-            const double bx = fma(v.inv[0], wx, fma(v.inv[1], wy, v.inv[3]));
-            const double by = fma(v.inv[4], wx, fma(v.inv[5], wy, v.inv[7]));
-            const double bz = fma(v.inv[8], wx, fma(v.inv[9], wy, v.inv[11]));
-            const int dx = v.dims[0], dy = v.dims[1], dz = v.dims[2];
-            const float dm1x = (float)(dx - 1), dm1y = (float)(dy - 1), dm1z = (float)(dz - 1);
-            const void* data = v.data;
-            const int dtype = v.dtype;
+            const ViewTile& t = s_vt[ai];
+            const bool staged = t.staged != 0;
+            if (staged) {
+                __syncthreads();  // previous view's taps are done with the stage buffers
+                stage_fixed_any(s_stage, t.data, t.dtype, t, tid);
+                if (use_content) stage_fixed(s_stage_c, t.content, t, tid);
+                __syncthreads();
+            }
+            if (!valid) continue;
+            // box-relative source coordinate of this thread's column at k = 0, and its z step
+            float rx = fmaf(t.m[0], tx, fmaf(t.m[1], ty, t.o[0]));
+            float ry = fmaf(t.m[3], tx, fmaf(t.m[4], ty, t.o[1]));
+            float rz = fmaf(t.m[6], tx, fmaf(t.m[7], ty, t.o[2]));
+            const float sxk = t.m[2], syk = t.m[5], szk = t.m[8];
+            const float bx = (float)t.b0[0], by = (float)t.b0[1], bz = (float)t.b0[2];
+            const float dm1x = (float)(t.dims[0] - 1), dm1y = (float)(t.dims[1] - 1), dm1z = (float)(t.dims[2] - 1);
+            const bool do_blend = use_blend && !t.plateau;
+            const bool interior = t.interior != 0;
 #pragma unroll
-            for (int k = 0; k < FUSE_ZT; ++k) {
-                if (z0 + k >= a.size[2]) break;
-                const double wz = (double)(a.bmin[2] + z0 + k);
-                const float sx = (float)fma(m02, wz, bx);
-                const float sy = (float)fma(m12, wz, by);
-                const float sz = (float)fma(m22, wz, bz);
-                if (!(sx >= 0.f && sx <= dm1x && sy >= 0.f && sy <= dm1y && sz >= 0.f && sz <= dm1z)) continue;
+            for (int k = 0; k < FUSE_ZT; ++k, rx += sxk, ry += syk, rz += szk) {
+                if (k >= nz) break;
+                const float fx = rx + bx, fy = ry + by, fz = rz + bz;  // absolute source coordinate
+                if (!(fx >= 0.f && fx <= dm1x && fy >= 0.f && fy <= dm1y && fz >= 0.f && fz <= dm1z)) continue;
                 float w = 1.f;
-                if (use_blend) {
-                    if (!blend_axis(sx, dm1x, v.border[0], v.range[0], a.lut_n, s_lut, w)) continue;
-                    if (!blend_axis(sy, dm1y, v.border[1], v.range[1], a.lut_n, s_lut, w)) continue;
-                    if (!blend_axis(sz, dm1z, v.border[2], v.range[2], a.lut_n, s_lut, w)) continue;
+                if (do_blend) {
+                    if (!blend_axis(fx, dm1x, t.border[0], t.inv_range[0], a.lut_n, s_lut, w)) continue;
+                    if (!blend_axis(fy, dm1y, t.border[1], t.inv_range[1], a.lut_n, s_lut, w)) continue;
+                    if (!blend_axis(fz, dm1z, t.border[2], t.inv_range[2], a.lut_n, s_lut, w)) continue;
                 }
-                const float val = sample_any<LINEAR>(data, dtype, dx, dy, dz, sx, sy, sz);
+                float val;
+                if (staged) val = interior ? sample_staged<true>(s_stage, t, fmaxf(rx, 0.f), fmaxf(ry, 0.f), fmaxf(rz, 0.f))
+                                           : sample_staged<false>(s_stage, t, fmaxf(rx, 0.f), fmaxf(ry, 0.f), fmaxf(rz, 0.f));
+                else val = sample_any<LINEAR>(t.data, t.dtype, t.dims[0], t.dims[1], t.dims[2], fx, fy, fz);
                 if (KIND == 0) {
-                    if (use_content) w *= sample<float, LINEAR>(v.content, dx, dy, dz, sx, sy, sz);
+                    if (use_content) {
+                        if (staged) w *= sample_staged<false>(s_stage_c, t, fmaxf(rx, 0.f), fmaxf(ry, 0.f), fmaxf(rz, 0.f));
+                        else w *= sample<float, LINEAR>(t.content, t.dims[0], t.dims[1], t.dims[2], fx, fy, fz);
+                    }
                     acc0[k] += w * val;
                     acc1[k] += w;
                 } else {
@@ -219,9 +388,8 @@ fuse_kernel(const FuseViewDev* __restrict__ views, int nviews, FuseArgs a) {
     if (!valid) return;
 #pragma unroll
     for (int k = 0; k < FUSE_ZT; ++k) {
-        const int z = z0 + k;
-        if (z >= a.size[2]) break;
-        const size_t o = ((size_t)z * a.size[1] + y) * a.size[0] + x;
+        if (k >= nz) break;
+        const size_t o = ((size_t)(z0 + k) * a.size[1] + y) * a.size[0] + x;
         if (ACCUM) {
             a.acc_wi[o] += acc0[k];
             a.acc_w[o] += acc1[k];
@@ -231,7 +399,7 @@ fuse_kernel(const FuseViewDev* __restrict__ views, int nviews, FuseArgs a) {
         if (KIND == 0) res = acc1[k] > 0.f ? acc0[k] / acc1[k] : 0.f;
         else res = acc1[k] > 0.f ? acc0[k] : 0.f;
         if (OUT == BS_DTYPE_F32) {
-            ((float*)a.out)[o] = res;
+            __stcs((float*)a.out + o, res);
         } else {
             double c = floor(((double)res - a.cmin) * a.cscale + 0.5);
             c = fmin(fmax(c, 0.0), a.ctop);
@@ -377,6 +545,10 @@ static int fuse_prepare(bs_ctx* ctx, const bs_view* views, int n_views, const lo
     a.ctop = p->out_dtype == BS_DTYPE_U8 ? 255.0 : 65535.0;
     a.cmin = p->min_intensity;
     a.cscale = p->out_dtype == BS_DTYPE_F32 ? 1.0 : a.ctop / (p->max_intensity - p->min_intensity);
+    {
+        const char* e = getenv("BS_FUSE_NO_STAGE");
+        a.no_stage = (e && *e && *e != '0') ? 1 : 0;
+    }
     prep->nviews = n_views;
     return BS_OK;
 }
@@ -384,9 +556,15 @@ static int fuse_prepare(bs_ctx* ctx, const bs_view* views, int n_views, const lo
 template <int KIND, bool LINEAR, bool ACCUM>
 static void launch_out(int out_dtype, dim3 grid, dim3 block, cudaStream_t s, const FuseViewDev* v, int n,
                        const FuseArgs& a) {
-    if (ACCUM || out_dtype == BS_DTYPE_F32) fuse_kernel<KIND, LINEAR, BS_DTYPE_F32, ACCUM><<<grid, block, 0, s>>>(v, n, a);
-    else if (out_dtype == BS_DTYPE_U16) fuse_kernel<KIND, LINEAR, BS_DTYPE_U16, false><<<grid, block, 0, s>>>(v, n, a);
-    else fuse_kernel<KIND, LINEAR, BS_DTYPE_U8, false><<<grid, block, 0, s>>>(v, n, a);
+    const bool content = a.fusion_type == BS_FUSE_AVG_CONTENT || a.fusion_type == BS_FUSE_AVG_BLEND_CONTENT;
+    const size_t dyn = content ? sizeof(float) * FS_N : 0;
+    auto go = [&](auto kern) {
+        if (dyn) cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+        kern<<<grid, block, dyn, s>>>(v, n, a);
+    };
+    if (ACCUM || out_dtype == BS_DTYPE_F32) go(fuse_kernel<KIND, LINEAR, BS_DTYPE_F32, ACCUM>);
+    else if (out_dtype == BS_DTYPE_U16) go(fuse_kernel<KIND, LINEAR, BS_DTYPE_U16, false>);
+    else go(fuse_kernel<KIND, LINEAR, BS_DTYPE_U8, false>);
 }
 
 static int fuse_launch(bs_ctx* ctx, const FusePrepared& prep, const bs_fuse_params* p, bool accum) {
