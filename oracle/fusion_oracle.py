@@ -271,6 +271,31 @@ def fuse_block(views, block_min_xyz, block_size_xyz, fusion_type=AVG_BLEND, inte
     return convert_output(out, out_dtype, min_intensity, max_intensity)
 
 
+def accumulate_block(views, block_min_xyz, block_size_xyz, fusion_type=AVG_BLEND, interpolation=1, blend_lut_n=0):
+    """Partial sums [sum w*I, sum w] of a view subset (the view-sharded mode of SURVEY.md 8e);
+    summing them over disjoint subsets and dividing equals fuse_block up to float re-association."""
+    bx, by, bz = block_size_xyz
+    sum_i = np.zeros((bz, by, bx), dtype=np.float32)
+    sum_w = np.zeros((bz, by, bx), dtype=np.float32)
+    for v in views:
+        dims_xyz = v.img.shape[::-1]
+        src = source_coords(v, block_min_xyz, block_size_xyz)
+        inside = inside_mask(src, dims_xyz)
+        if not inside.any():
+            continue
+        val = trilinear(v.img, src) if interpolation == 1 else nearest(v.img, src)
+        if fusion_type in (AVG_BLEND, AVG_BLEND_CONTENT):
+            w = blend_weight(src, dims_xyz, v.blend_border, v.blend_range, blend_lut_n)
+        else:
+            w = inside.astype(np.float32)
+        w = np.where(inside, w, np.float32(0)).astype(np.float32)
+        if fusion_type in (AVG_CONTENT, AVG_BLEND_CONTENT):
+            w = (w * trilinear(v.content, src)).astype(np.float32)
+        sum_i = (sum_i + w * val).astype(np.float32)
+        sum_w = (sum_w + w).astype(np.float32)
+    return sum_i, sum_w
+
+
 def convert_output(out, out_dtype, min_intensity, max_intensity):
     """float32 stays; RealUnsignedByte/ShortConverter(min,max): round((v-min)/(max-min)*
     {255|65535}) clamped (SparkAffineFusion.java:493-517).  Rounding is Java Math.round-like
