@@ -167,6 +167,371 @@ __global__ void __launch_bounds__(PCM_THREADS) k_fft_x_r2c(const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------
+// x pass, real -> complex, persistent + TMA: each CTA loops over line groups; the raw uint16 /
+// float rows of the NEXT group are pulled into shared memory by the TMA unit (1-D bulk copies
+// completing on an mbarrier) while the current group is windowed, transformed and stored.
+__device__ __forceinline__ unsigned int smem_u32(const void* p) {
+    return (unsigned int)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct XR2CTmaArgs {
+    XR2CArgs x;
+    int n_groups;      // line groups per plane
+    int n_items;       // 2 * Pz * n_groups
+    int row_bytes;     // dx * element size (multiple of 16)
+    int esize;
+};
+
+template <class F>
+__global__ void __launch_bounds__(PCM_THREADS) k_fft_x_r2c_tma(const __grid_constant__ XR2CTmaArgs t) {
+    const XR2CArgs& a = t.x;
+    const int M = F::kStatic ? F::N : a.M;
+    const int lshift = F::kStatic ? F::LSHIFT : a.lshift;
+    const int LB = 1 << lshift, ls = LB + 1;
+    const int Px = 2 * M;
+    const int pitch = F::kStatic ? ((F::N + 1 + 15) / 16) * 16 : a.pitch;
+    float2* tw = bs_sm;
+    float2* b0 = bs_sm + Px;
+    float2* b1 = b0 + M * ls;
+    unsigned char* raw = reinterpret_cast<unsigned char*>(b1 + M * ls);     // 2 * LB * row_bytes, 16-B aligned
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(raw + 2 * (size_t)LB * t.row_bytes);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int NW = PCM_THREADS / 32;
+
+    for (int i = threadIdx.x; i < Px; i += blockDim.x) tw[i] = a.tw[i];
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // item -> (image, plane, line group); consecutive items share the plane
+    auto decode = [&](int w, int& im, int& zp, int& y0) {
+        const int g = w % t.n_groups;
+        const int r = w / t.n_groups;
+        zp = r % a.Pz;
+        im = r / a.Pz;
+        y0 = g * LB;
+    };
+    // producer: issue the bulk copies of item w into stage buffer `buf` (thread 0 only)
+    auto prefetch = [&](int w, int buf) {
+        int im, zp, y0;
+        decode(w, im, zp, y0);
+        if (zp >= a.Ez || y0 >= a.Ey) return;
+        const int nl = min(min(LB, a.Py - y0), a.Ey - y0);
+        mbar_expect_tx(&bars[buf], (unsigned int)(nl * t.row_bytes));
+        const unsigned char* img = reinterpret_cast<const unsigned char*>(a.img[im]);
+        const int sz = a.idx_z[zp];
+        for (int l = 0; l < nl; ++l) {
+            const size_t row = (size_t)sz * a.dy + a.idx_y[y0 + l];
+            tma_bulk_g2s(raw + ((size_t)buf * LB + l) * t.row_bytes, img + row * t.row_bytes, (unsigned int)t.row_bytes,
+                         &bars[buf]);
+        }
+    };
+
+    unsigned int phase[2] = {0u, 0u};
+    int it = 0;
+    if (threadIdx.x == 0 && (int)blockIdx.x < t.n_items) prefetch(blockIdx.x, 0);
+    for (int w = blockIdx.x; w < t.n_items; w += gridDim.x, ++it) {
+        const int buf = it & 1;
+        int im, zp, y0;
+        decode(w, im, zp, y0);
+        const int wn = w + gridDim.x;
+        if (threadIdx.x == 0 && wn < t.n_items) prefetch(wn, buf ^ 1);
+        float2* __restrict__ spec = a.spec[im];
+        const size_t rowbase = ((size_t)zp * a.Py + y0) * pitch;
+        const int nlines = min(LB, a.Py - y0);
+        if (zp >= a.Ez || y0 >= a.Ey) {  // zero padding: no loads were issued for this item
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            float4* d4 = reinterpret_cast<float4*>(spec + rowbase);
+            for (int i = threadIdx.x; i < nlines * (pitch >> 1); i += blockDim.x) d4[i] = z4;
+            continue;
+        }
+        mbar_wait(&bars[buf], phase[buf]);
+        phase[buf] ^= 1u;
+        const float wz = a.w_z[zp];
+        const int e0 = a.ex;
+        const unsigned char* rb = raw + (size_t)buf * LB * t.row_bytes;
+        // window + pack from the staged rows
+        for (int l = wid; l < LB; l += NW) {
+            const int yp = y0 + l;
+            const bool live = l < nlines && yp < a.Ey;
+            const float wy = live ? a.w_y[yp] : 0.f;
+            const float gyz = wy * wz;
+            const unsigned char* row = rb + (size_t)l * t.row_bytes;
+            for (int n = lane; n < M; n += 32) {
+                float2 v = make_float2(0.f, 0.f);
+                if (live) {
+                    const int xp = 2 * n;
+                    if (xp >= e0 && xp + 1 < e0 + a.dx) {
+                        const int xs = xp - e0;
+                        float p0, p1;
+                        if (a.dtype == BS_DTYPE_U16) {
+                            p0 = (float)reinterpret_cast<const unsigned short*>(row)[xs];
+                            p1 = (float)reinterpret_cast<const unsigned short*>(row)[xs + 1];
+                        } else if (a.dtype == BS_DTYPE_F32) {
+                            p0 = reinterpret_cast<const float*>(row)[xs];
+                            p1 = reinterpret_cast<const float*>(row)[xs + 1];
+                        } else {
+                            p0 = (float)row[xs];
+                            p1 = (float)row[xs + 1];
+                        }
+                        v = make_float2(p0 * gyz, p1 * gyz);
+                    } else if (xp < a.Ex) {
+                        const float g0 = (a.w_x[xp] * wy) * wz, g1 = (a.w_x[xp + 1] * wy) * wz;
+                        const int i0 = a.idx_x[xp], i1 = a.idx_x[xp + 1];
+                        float p0, p1;
+                        if (a.dtype == BS_DTYPE_U16) {
+                            p0 = (float)reinterpret_cast<const unsigned short*>(row)[i0];
+                            p1 = (float)reinterpret_cast<const unsigned short*>(row)[i1];
+                        } else if (a.dtype == BS_DTYPE_F32) {
+                            p0 = reinterpret_cast<const float*>(row)[i0];
+                            p1 = reinterpret_cast<const float*>(row)[i1];
+                        } else {
+                            p0 = (float)row[i0];
+                            p1 = (float)row[i1];
+                        }
+                        v = make_float2(g0 != 0.f ? p0 * g0 : 0.f, g1 != 0.f ? p1 * g1 : 0.f);
+                    }
+                }
+                b0[n * ls + l] = v;
+            }
+        }
+        __syncthreads();
+        const float2* res = F::run(b0, b1, tw, a.plan, lshift, ls, 2);
+        for (int l = wid; l < nlines; l += NW) {
+            float2* srow = spec + rowbase + (size_t)l * pitch;
+            for (int k = lane; k < pitch; k += 32) {
+                float2 X = make_float2(0.f, 0.f);
+                if (k <= M) {
+                    const int k0 = (k == M) ? 0 : k;
+                    const int k1 = (k == 0 || k == M) ? 0 : M - k;
+                    const float2 Zk = res[k0 * ls + l];
+                    float2 Zm = res[k1 * ls + l];
+                    Zm.y = -Zm.y;
+                    const float2 E = make_float2(0.5f * (Zk.x + Zm.x), 0.5f * (Zk.y + Zm.y));
+                    const float2 D = make_float2(0.5f * (Zk.x - Zm.x), 0.5f * (Zk.y - Zm.y));
+                    const float2 wD = cmulf(tw[k], D);
+                    X = make_float2(E.x + wD.y, E.y - wD.x);
+                }
+                __stcg(srow + k, X);
+            }
+        }
+        __syncthreads();  // b0/b1 and the consumed stage buffer may be overwritten from here on
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+struct XC2RArgs {
+    float2* spec;
+    int Px, Py, Pz, M, pitch;
+    const float2* tw;
+    FftPlan plan;
+    int lshift;
+    float scale;
+};
+
+// Warp-private x passes: one warp owns one line at a time (window, FFT, untangle, store) with
+// only __syncwarp() between steps; the raw row of the warp's NEXT line is fetched by a 1-D bulk
+// TMA copy into the warp's own double buffer (own mbarrier), so there is no block-wide barrier
+// in the steady state and the 8 warps of a CTA overlap each other's memory and math phases.
+struct XWArgs {
+    XR2CArgs x;
+    int row_bytes;     // dx * element size; multiple of 16 when use_tma
+    int use_tma;
+    long long n_lines; // 2 * Pz * Py
+};
+
+__device__ __forceinline__ float raw_elem(const unsigned char* row, int dtype, int i) {
+    if (dtype == BS_DTYPE_U16) return (float)reinterpret_cast<const unsigned short*>(row)[i];
+    if (dtype == BS_DTYPE_F32) return reinterpret_cast<const float*>(row)[i];
+    return (float)row[i];
+}
+
+template <class F>
+__global__ void __launch_bounds__(PCM_THREADS) k_fft_x_r2c_w(const __grid_constant__ XWArgs t) {
+    const XR2CArgs& a = t.x;
+    const int M = F::kStatic ? F::N : a.M;
+    const int Px = 2 * M;
+    const int pitch = F::kStatic ? ((F::N + 1 + 15) / 16) * 16 : a.pitch;
+    constexpr int NW = PCM_THREADS / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // smem: tw[Px] | per warp: A[M], B[M] | per warp raw[2][row_bytes] | per warp mbar[2]
+    float2* tw = bs_sm;
+    float2* A = bs_sm + Px + (size_t)wid * 2 * M;
+    float2* B = A + M;
+    unsigned char* raw = reinterpret_cast<unsigned char*>(bs_sm + Px + (size_t)NW * 2 * M) + (size_t)wid * 2 * t.row_bytes;
+    unsigned long long* bars =
+        reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(bs_sm + Px + (size_t)NW * 2 * M) +
+                                              (size_t)NW * 2 * t.row_bytes) + 2 * wid;
+    for (int i = threadIdx.x; i < Px; i += blockDim.x) tw[i] = a.tw[i];
+    if (t.use_tma && lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long gw = (long long)blockIdx.x * NW + wid, gstride = (long long)gridDim.x * NW;
+    const int e0 = a.ex;
+    // line -> (image, plane, row); returns the source row index or -1 for an all-zero line
+    auto src_row = [&](long long line, int& im, int& zp, int& yp) -> long long {
+        yp = (int)(line % a.Py);
+        const long long r = line / a.Py;
+        zp = (int)(r % a.Pz);
+        im = (int)(r / a.Pz);
+        if (zp >= a.Ez || yp >= a.Ey) return -1;
+        return (long long)a.idx_z[zp] * a.dy + a.idx_y[yp];
+    };
+    auto prefetch = [&](long long line, int buf) {  // lane 0 only
+        int im, zp, yp;
+        const long long row = src_row(line, im, zp, yp);
+        if (row < 0) return;
+        const unsigned char* img = reinterpret_cast<const unsigned char*>(a.img[im]);
+        mbar_expect_tx(&bars[buf], (unsigned int)t.row_bytes);
+        tma_bulk_g2s(raw + (size_t)buf * t.row_bytes, img + (size_t)row * t.row_bytes, (unsigned int)t.row_bytes, &bars[buf]);
+    };
+
+    unsigned int phase0 = 0u, phase1 = 0u;
+    int it = 0;
+    if (t.use_tma && lane == 0 && gw < t.n_lines) prefetch(gw, 0);
+    for (long long line = gw; line < t.n_lines; line += gstride, ++it) {
+        const int buf = it & 1;
+        if (t.use_tma && lane == 0 && line + gstride < t.n_lines) prefetch(line + gstride, buf ^ 1);
+        int im, zp, yp;
+        const long long row = src_row(line, im, zp, yp);
+        float2* srow = a.spec[im] + ((size_t)zp * a.Py + yp) * pitch;
+        if (row < 0) {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = lane; i < (pitch >> 1); i += 32) reinterpret_cast<float4*>(srow)[i] = z4;
+            continue;
+        }
+        const float wy = a.w_y[yp], wz = a.w_z[zp];
+        const float gyz = wy * wz;
+        const unsigned char* rrow;
+        if (t.use_tma) {
+            mbar_wait(&bars[buf], buf ? phase1 : phase0);
+            if (buf) phase1 ^= 1u; else phase0 ^= 1u;
+            rrow = raw + (size_t)buf * t.row_bytes;
+        } else {
+            rrow = reinterpret_cast<const unsigned char*>(a.img[im]) + (size_t)row * t.row_bytes;  // global
+        }
+        for (int n = lane; n < M; n += 32) {
+            float2 v = make_float2(0.f, 0.f);
+            const int xp = 2 * n;
+            if (xp >= e0 && xp + 1 < e0 + a.dx) {
+                v = make_float2(raw_elem(rrow, a.dtype, xp - e0) * gyz, raw_elem(rrow, a.dtype, xp - e0 + 1) * gyz);
+            } else if (xp < a.Ex) {
+                const float g0 = (a.w_x[xp] * wy) * wz, g1 = (a.w_x[xp + 1] * wy) * wz;
+                const float p0 = raw_elem(rrow, a.dtype, a.idx_x[xp]), p1 = raw_elem(rrow, a.dtype, a.idx_x[xp + 1]);
+                v = make_float2(g0 != 0.f ? p0 * g0 : 0.f, g1 != 0.f ? p1 * g1 : 0.f);
+            }
+            A[n] = v;
+        }
+        __syncwarp();
+        const float2* res = F::run(A, B, tw, a.plan, 2, lane);
+        for (int k = lane; k < pitch; k += 32) {
+            float2 X = make_float2(0.f, 0.f);
+            if (k <= M) {
+                const int k0 = (k == M) ? 0 : k;
+                const int k1 = (k == 0 || k == M) ? 0 : M - k;
+                const float2 Zk = res[k0];
+                float2 Zm = res[k1];
+                Zm.y = -Zm.y;
+                const float2 E = make_float2(0.5f * (Zk.x + Zm.x), 0.5f * (Zk.y + Zm.y));
+                const float2 D = make_float2(0.5f * (Zk.x - Zm.x), 0.5f * (Zk.y - Zm.y));
+                const float2 wD = cmulf(tw[k], D);
+                X = make_float2(E.x + wD.y, E.y - wD.x);
+            }
+            __stcg(srow + k, X);
+        }
+        __syncwarp();  // A/B and the consumed raw buffer are free again
+    }
+}
+
+#define XW_MAXV 10   // float2 per lane covering a row of up to 32 * XW_MAXV spectrum entries
+template <class F>
+__global__ void __launch_bounds__(PCM_THREADS) k_fft_x_c2r_w(const __grid_constant__ XC2RArgs a) {
+    const int M = F::kStatic ? F::N : a.M;
+    const int Px = 2 * M;
+    const int pitch = F::kStatic ? ((F::N + 1 + 15) / 16) * 16 : a.pitch;
+    constexpr int NW = PCM_THREADS / 32;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float2* tw = bs_sm;
+    float2* A = bs_sm + Px + (size_t)wid * 2 * (M + 1);   // M + 1 entries each
+    float2* B = A + (M + 1);
+    for (int i = threadIdx.x; i < Px; i += blockDim.x) tw[i] = a.tw[i];
+    __syncthreads();
+    const long long n_lines = (long long)a.Py * a.Pz;
+    const long long gw = (long long)blockIdx.x * NW + wid, gstride = (long long)gridDim.x * NW;
+    float2 nxt[XW_MAXV];
+    auto load_row = [&](long long line) {
+        const float2* srow = a.spec + (size_t)line * pitch;
+#pragma unroll
+        for (int u = 0; u < XW_MAXV; ++u) {
+            const int k = lane + 32 * u;
+            nxt[u] = (k <= M) ? __ldcg(srow + k) : make_float2(0.f, 0.f);
+        }
+    };
+    if (gw < n_lines) load_row(gw);
+    for (long long line = gw; line < n_lines; line += gstride) {
+        // spectrum row -> B (conjugated: partial inverse along y,z = conj of forward transforms of conj data)
+#pragma unroll
+        for (int u = 0; u < XW_MAXV; ++u) {
+            const int k = lane + 32 * u;
+            if (k <= M) B[k] = make_float2(nxt[u].x, -nxt[u].y);
+        }
+        __syncwarp();
+        if (line + gstride < n_lines) load_row(line + gstride);   // prefetch into registers
+        for (int k = lane; k < M; k += 32) {
+            const float2 Xk = B[k];
+            float2 Xm = B[M - k];
+            Xm.y = -Xm.y;
+            const float2 E = make_float2(0.5f * (Xk.x + Xm.x), 0.5f * (Xk.y + Xm.y));
+            const float2 D = make_float2(0.5f * (Xk.x - Xm.x), 0.5f * (Xk.y - Xm.y));
+            float2 w = tw[k];
+            w.y = -w.y;
+            const float2 O = cmulf(D, w);
+            A[k] = make_float2(E.x - O.y, -(E.y + O.x));
+        }
+        __syncwarp();
+        const float2* res = F::run(A, B, tw, a.plan, 2, lane);
+        float2* row = a.spec + (size_t)line * pitch;
+        for (int n = lane; n < M; n += 32) {
+            const float2 r = res[n];
+            __stcg(row + n, make_float2(r.x * a.scale, -r.y * a.scale));
+        }
+        __syncwarp();
+    }
+}
+
+typedef FftWStatic<270, 2, 9, 6, 5> FftW270;
+
+// ------------------------------------------------------------------------------------------
 // strided passes (y and z)
 struct StridedArgs {
     float2* a;
@@ -213,13 +578,13 @@ __device__ __forceinline__ void tile_store(float2* g, const float2* src, long lo
 
 __device__ __forceinline__ float2 unit_or_zero(float2 x, float thresh) {
     const float m2 = x.x * x.x + x.y * x.y;
-    const float m = sqrtf(m2);
-    if (m < thresh) return make_float2(0.f, 0.f);
-    return make_float2(x.x / m, x.y / m);
+    if (m2 < thresh * thresh) return make_float2(0.f, 0.f);   // |x| < threshold
+    const float inv = rsqrtf(m2);
+    return make_float2(x.x * inv, x.y * inv);
 }
 
 template <class F>
-__global__ void __launch_bounds__(PCM_THREADS) k_fft_strided(const __grid_constant__ StridedArgs a) {
+__global__ void __launch_bounds__(PCM_THREADS, 3) k_fft_strided(const __grid_constant__ StridedArgs a) {
     const int tshift = F::kStatic ? F::LSHIFT : a.tshift;
     const int TW = 1 << tshift, N = F::kStatic ? F::N : a.plan.n;
     const int twpad = (N + 1) & ~1;
@@ -257,14 +622,6 @@ __global__ void __launch_bounds__(PCM_THREADS) k_fft_strided(const __grid_consta
 
 // ------------------------------------------------------------------------------------------
 // x pass, complex -> real, in place
-struct XC2RArgs {
-    float2* spec;
-    int Px, Py, Pz, M, pitch;
-    const float2* tw;
-    FftPlan plan;
-    int lshift;
-    float scale;
-};
 
 template <class F>
 __global__ void __launch_bounds__(PCM_THREADS) k_fft_x_c2r(const __grid_constant__ XC2RArgs a) {
@@ -491,79 +848,147 @@ struct PearsonArgs {
     double* sums_d;              // same for float input
 };
 
-template <typename T>
-__device__ __forceinline__ void pearson_int(const PearsonArgs& a, const PearsonCand& c, unsigned long long* out) {
+// Row-chunk-major traversal: a warp owns PR_ROWS consecutive rows of image 1 and evaluates EVERY
+// candidate on them before moving on, so all candidates stream through the volumes in lockstep and
+// the second..K-th read of a row is an L1/L2 hit (DRAM traffic ~ one sweep instead of K sweeps).
+#define PR_ROWS 8
+
+__device__ __forceinline__ void pr_acc(unsigned int va, unsigned int vb, unsigned int& ra, unsigned int& rb,
+                                       unsigned long long& saa, unsigned long long& sbb, unsigned long long& sab) {
+    ra += va;
+    rb += vb;
+    saa += (unsigned long long)(va * va);
+    sbb += (unsigned long long)(vb * vb);
+    sab += (unsigned long long)(va * vb);
+}
+
+__device__ __forceinline__ void pearson_u16(const PearsonArgs& a, int ncand, unsigned long long* s_acc) {
+    const unsigned short* __restrict__ i1 = (const unsigned short*)a.img1;
+    const unsigned short* __restrict__ i2 = (const unsigned short*)a.img2;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const long long nrows = (long long)a.dy * a.dz;
+    const long long nchunks = (nrows + PR_ROWS - 1) / PR_ROWS;
+    const bool even_rows = !(a.dx & 1) && !((size_t)i1 & 3) && !((size_t)i2 & 3);
+    for (long long ch = (long long)blockIdx.x * nw + wid; ch < nchunks; ch += (long long)gridDim.x * nw) {
+        const long long r0 = ch * PR_ROWS;
+        for (int c = 0; c < ncand; ++c) {
+            const PearsonCand cd = a.cands[c];
+            unsigned long long sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
+            bool any = false;
+            // both x offsets even -> aligned ushort2 loads on both images
+            const bool vec = even_rows && !((cd.o1[0] | cd.o2[0]) & 1);
+            for (int rr = 0; rr < PR_ROWS; ++rr) {
+                const long long r = r0 + rr;
+                if (r >= nrows) break;
+                const int z = (int)(r / a.dy), y = (int)(r - (long long)z * a.dy);
+                const int yy = y - cd.o1[1], zz = z - cd.o1[2];
+                if (yy < 0 || yy >= cd.sz[1] || zz < 0 || zz >= cd.sz[2]) continue;
+                any = true;
+                const unsigned short* p1 = i1 + (size_t)r * a.dx + cd.o1[0];
+                const unsigned short* p2 = i2 + ((size_t)(zz + cd.o2[2]) * a.dy + (yy + cd.o2[1])) * a.dx + cd.o2[0];
+                unsigned int ra = 0, rb = 0;
+                const int n = cd.sz[0];
+                if (vec) {
+                    const unsigned int* q1 = reinterpret_cast<const unsigned int*>(p1);
+                    const unsigned int* q2 = reinterpret_cast<const unsigned int*>(p2);
+                    const int nv = n >> 1;
+#pragma unroll 4
+                    for (int x = lane; x < nv; x += 32) {
+                        const unsigned int w1 = __ldg(q1 + x), w2 = __ldg(q2 + x);
+                        pr_acc(w1 & 0xffffu, w2 & 0xffffu, ra, rb, saa, sbb, sab);
+                        pr_acc(w1 >> 16, w2 >> 16, ra, rb, saa, sbb, sab);
+                    }
+                    if ((n & 1) && lane == 0) pr_acc(__ldg(p1 + n - 1), __ldg(p2 + n - 1), ra, rb, saa, sbb, sab);
+                } else if (even_rows && n >= 4) {
+                    // exactly one x offset is odd: aligned words on one side, funnel-shifted pairs of
+                    // aligned words on the other (element -1 and the following words stay inside the row)
+                    const bool odd1 = cd.o1[0] & 1;
+                    const unsigned int* qa = reinterpret_cast<const unsigned int*>(odd1 ? p2 : p1);
+                    const unsigned int* qm = reinterpret_cast<const unsigned int*>((odd1 ? p1 : p2) - 1);
+                    const int nv = (n >> 1) - 1;  // last pair(s) handled below: qm[x + 1] must not leave the row
+#pragma unroll 4
+                    for (int x = lane; x < nv; x += 32) {
+                        const unsigned int wa = __ldg(qa + x);
+                        const unsigned int wm = __funnelshift_r(__ldg(qm + x), __ldg(qm + x + 1), 16);
+                        const unsigned int a0 = odd1 ? (wm & 0xffffu) : (wa & 0xffffu), a1 = odd1 ? (wm >> 16) : (wa >> 16);
+                        const unsigned int b0 = odd1 ? (wa & 0xffffu) : (wm & 0xffffu), b1 = odd1 ? (wa >> 16) : (wm >> 16);
+                        pr_acc(a0, b0, ra, rb, saa, sbb, sab);
+                        pr_acc(a1, b1, ra, rb, saa, sbb, sab);
+                    }
+                    for (int x = 2 * nv + lane; x < n; x += 32) pr_acc(__ldg(p1 + x), __ldg(p2 + x), ra, rb, saa, sbb, sab);
+                } else {
+#pragma unroll 4
+                    for (int x = lane; x < n; x += 32) pr_acc(__ldg(p1 + x), __ldg(p2 + x), ra, rb, saa, sbb, sab);
+                }
+                sa += ra;
+                sb += rb;
+            }
+            if (!any) continue;  // warp-uniform
+            unsigned long long v[5] = {sa, sb, saa, sbb, sab};
+#pragma unroll
+            for (int k = 0; k < 5; ++k) {
+                unsigned long long t = v[k];
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
+                if (lane == 0 && t) atomicAdd(&s_acc[5 * c + k], t);
+            }
+        }
+    }
+}
+
+template <typename T, typename ACC>
+__device__ __forceinline__ void pearson_generic(const PearsonArgs& a, int ncand, ACC* s_acc) {
     const T* __restrict__ i1 = (const T*)a.img1;
     const T* __restrict__ i2 = (const T*)a.img2;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    unsigned long long sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
-    const long long rows = (long long)c.sz[1] * c.sz[2];
-    for (long long r = (long long)blockIdx.x * nw + wid; r < rows; r += (long long)gridDim.x * nw) {
-        const int zz = (int)(r / c.sz[1]), yy = (int)(r - (long long)zz * c.sz[1]);
-        const T* p1 = i1 + ((size_t)(zz + c.o1[2]) * a.dy + (yy + c.o1[1])) * a.dx + c.o1[0];
-        const T* p2 = i2 + ((size_t)(zz + c.o2[2]) * a.dy + (yy + c.o2[1])) * a.dx + c.o2[0];
-        unsigned int ra = 0, rb = 0;
-#pragma unroll 4
-        for (int x = lane; x < c.sz[0]; x += 32) {
-            const unsigned int va = __ldg(p1 + x), vb = __ldg(p2 + x);
-            ra += va;
-            rb += vb;
-            saa += (unsigned long long)(va * va);
-            sbb += (unsigned long long)(vb * vb);
-            sab += (unsigned long long)(va * vb);
-        }
-        sa += ra;
-        sb += rb;
-    }
-    __shared__ unsigned long long s_acc[5];
-    if (threadIdx.x < 5) s_acc[threadIdx.x] = 0;
-    __syncthreads();
-    unsigned long long v[5] = {sa, sb, saa, sbb, sab};
+    const long long nrows = (long long)a.dy * a.dz;
+    const long long nchunks = (nrows + PR_ROWS - 1) / PR_ROWS;
+    for (long long ch = (long long)blockIdx.x * nw + wid; ch < nchunks; ch += (long long)gridDim.x * nw) {
+        const long long r0 = ch * PR_ROWS;
+        for (int c = 0; c < ncand; ++c) {
+            const PearsonCand cd = a.cands[c];
+            ACC v[5] = {0, 0, 0, 0, 0};
+            bool any = false;
+            for (int rr = 0; rr < PR_ROWS; ++rr) {
+                const long long r = r0 + rr;
+                if (r >= nrows) break;
+                const int z = (int)(r / a.dy), y = (int)(r - (long long)z * a.dy);
+                const int yy = y - cd.o1[1], zz = z - cd.o1[2];
+                if (yy < 0 || yy >= cd.sz[1] || zz < 0 || zz >= cd.sz[2]) continue;
+                any = true;
+                const T* p1 = i1 + (size_t)r * a.dx + cd.o1[0];
+                const T* p2 = i2 + ((size_t)(zz + cd.o2[2]) * a.dy + (yy + cd.o2[1])) * a.dx + cd.o2[0];
+                for (int x = lane; x < cd.sz[0]; x += 32) {
+                    const ACC va = (ACC)__ldg(p1 + x), vb = (ACC)__ldg(p2 + x);
+                    v[0] += va; v[1] += vb; v[2] += va * va; v[3] += vb * vb; v[4] += va * vb;
+                }
+            }
+            if (!any) continue;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        unsigned long long s = v[k];
+            for (int k = 0; k < 5; ++k) {
+                ACC t = v[k];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-        if (lane == 0) atomicAdd(&s_acc[k], s);
-    }
-    __syncthreads();
-    if (threadIdx.x < 5 && s_acc[threadIdx.x]) atomicAdd(out + threadIdx.x, s_acc[threadIdx.x]);
-}
-
-__device__ __forceinline__ void pearson_flt(const PearsonArgs& a, const PearsonCand& c, double* out) {
-    const float* __restrict__ i1 = (const float*)a.img1;
-    const float* __restrict__ i2 = (const float*)a.img2;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    double v[5] = {0, 0, 0, 0, 0};
-    const long long rows = (long long)c.sz[1] * c.sz[2];
-    for (long long r = (long long)blockIdx.x * nw + wid; r < rows; r += (long long)gridDim.x * nw) {
-        const int zz = (int)(r / c.sz[1]), yy = (int)(r - (long long)zz * c.sz[1]);
-        const float* p1 = i1 + ((size_t)(zz + c.o1[2]) * a.dy + (yy + c.o1[1])) * a.dx + c.o1[0];
-        const float* p2 = i2 + ((size_t)(zz + c.o2[2]) * a.dy + (yy + c.o2[1])) * a.dx + c.o2[0];
-        for (int x = lane; x < c.sz[0]; x += 32) {
-            const double va = __ldg(p1 + x), vb = __ldg(p2 + x);
-            v[0] += va; v[1] += vb; v[2] += va * va; v[3] += vb * vb; v[4] += va * vb;
+                for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xffffffffu, t, off);
+                if (lane == 0) atomicAdd(&s_acc[5 * c + k], t);
+            }
         }
     }
-    __shared__ double s_accd[5];
-    if (threadIdx.x < 5) s_accd[threadIdx.x] = 0.0;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-        double s = v[k];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
-        if (lane == 0) atomicAdd(&s_accd[k], s);
-    }
-    __syncthreads();
-    if (threadIdx.x < 5) atomicAdd(out + threadIdx.x, s_accd[threadIdx.x]);
 }
 
-__global__ void __launch_bounds__(PCM_THREADS) k_pearson(const __grid_constant__ PearsonArgs a) {
-    const PearsonCand c = a.cands[blockIdx.y];
-    if (a.dtype == BS_DTYPE_U16) pearson_int<unsigned short>(a, c, a.sums_u + 5 * blockIdx.y);
-    else if (a.dtype == BS_DTYPE_U8) pearson_int<unsigned char>(a, c, a.sums_u + 5 * blockIdx.y);
-    else pearson_flt(a, c, a.sums_d + 5 * blockIdx.y);
+// dynamic smem: 5 accumulators per candidate (8 bytes each)
+__global__ void __launch_bounds__(PCM_THREADS) k_pearson(const __grid_constant__ PearsonArgs a, int ncand) {
+    unsigned long long* s_u = reinterpret_cast<unsigned long long*>(bs_sm);
+    double* s_d = reinterpret_cast<double*>(bs_sm);
+    for (int i = threadIdx.x; i < 5 * ncand; i += blockDim.x) s_u[i] = 0ull;  // 0.0 has the same bit pattern
+    __syncthreads();
+    if (a.dtype == BS_DTYPE_U16) pearson_u16(a, ncand, s_u);
+    else if (a.dtype == BS_DTYPE_U8) pearson_generic<unsigned char, unsigned long long>(a, ncand, s_u);
+    else pearson_generic<float, double>(a, ncand, s_d);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 5 * ncand; i += blockDim.x) {
+        if (a.dtype == BS_DTYPE_F32) { if (s_d[i] != 0.0) atomicAdd(a.sums_d + i, s_d[i]); }
+        else if (s_u[i]) atomicAdd(a.sums_u + i, s_u[i]);
+    }
 }
 
 // ==========================================================================================
@@ -803,6 +1228,13 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftGeneric>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c<FftX270>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c<FftX270L8>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c_tma<FftX270L8>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c_w<FftW270>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c_w<FftWGeneric>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r_w<FftW270>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r_w<FftWGeneric>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c_tma<FftX270>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c_tma<FftGeneric>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftX270L8>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_strided<FftS540>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftX270>, 0))) return rc;
@@ -829,7 +1261,37 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         const int LB = 1 << g.lshift_r2c;
         dim3 grid((g.P[1] + LB - 1) / LB, g.P[2], 2);
         bs_launch_scope sc(ctx, "fft_x_r2c");
-        if (g.static_x && g.lshift_r2c == 3) k_fft_x_r2c<FftX270L8><<<grid, PCM_THREADS, g.smem_x_r2c, ctx->stream>>>(a);
+        const int esize = dtype == BS_DTYPE_U16 ? 2 : dtype == BS_DTYPE_F32 ? 4 : 1;
+        const int row_bytes = g.d[0] * esize;
+        const size_t smem_tma = g.smem_x_r2c + 2 * (size_t)LB * row_bytes + 16;
+        const bool tma_ok = env_int("BS_FFT_R2C_TMA", 1) != 0 && (row_bytes % 16) == 0 && ((size_t)d1 % 16) == 0 &&
+                            ((size_t)d2 % 16) == 0 && smem_tma <= PCM_SMEM_MAX && (g.smem_x_r2c % 16) == 0;
+        const int xmode = env_int("BS_FFT_X_WARP", 1);
+        const size_t smem_w = ((size_t)g.P[0] + (size_t)(PCM_THREADS / 32) * 2 * g.M) * sizeof(float2) +
+                              (tma_ok ? (size_t)(PCM_THREADS / 32) * (2 * (size_t)row_bytes + 16) : 0);
+        if (xmode && g.M <= 32 * XW_MAXV - 1 && smem_w <= PCM_SMEM_MAX && (((size_t)g.P[0] + 16 * (size_t)g.M) * 8) % 16 == 0) {
+            XWArgs t;
+            t.x = a;
+            t.row_bytes = row_bytes;
+            t.use_tma = tma_ok ? 1 : 0;
+            t.n_lines = 2LL * g.P[2] * g.P[1];
+            const int per_sm = std::max(1, std::min(6, (int)(PCM_SMEM_MAX / (smem_w + 1024))));
+            const int nctas = (int)std::min<long long>((t.n_lines + 7) / 8, (long long)ctx->sm_count * per_sm);
+            if (g.M == FftW270::N && env_int("BS_FFT_STATIC", 1)) k_fft_x_r2c_w<FftW270><<<nctas, PCM_THREADS, smem_w, ctx->stream>>>(t);
+            else k_fft_x_r2c_w<FftWGeneric><<<nctas, PCM_THREADS, smem_w, ctx->stream>>>(t);
+        } else if (tma_ok) {
+            XR2CTmaArgs t;
+            t.x = a;
+            t.n_groups = (g.P[1] + LB - 1) / LB;
+            t.n_items = 2 * g.P[2] * t.n_groups;
+            t.row_bytes = row_bytes;
+            t.esize = esize;
+            const int per_sm = std::max(1, (int)(PCM_SMEM_MAX / (smem_tma + 1024)));
+            const int nctas = std::min(t.n_items, ctx->sm_count * std::min(per_sm, 4));
+            if (g.static_x && g.lshift_r2c == 3) k_fft_x_r2c_tma<FftX270L8><<<nctas, PCM_THREADS, smem_tma, ctx->stream>>>(t);
+            else if (g.static_x && g.lshift_r2c == 4) k_fft_x_r2c_tma<FftX270><<<nctas, PCM_THREADS, smem_tma, ctx->stream>>>(t);
+            else k_fft_x_r2c_tma<FftGeneric><<<nctas, PCM_THREADS, smem_tma, ctx->stream>>>(t);
+        } else if (g.static_x && g.lshift_r2c == 3) k_fft_x_r2c<FftX270L8><<<grid, PCM_THREADS, g.smem_x_r2c, ctx->stream>>>(a);
         else if (g.static_x && g.lshift_r2c == 4) k_fft_x_r2c<FftX270><<<grid, PCM_THREADS, g.smem_x_r2c, ctx->stream>>>(a);
         else k_fft_x_r2c<FftGeneric><<<grid, PCM_THREADS, g.smem_x_r2c, ctx->stream>>>(a);
     }
@@ -893,7 +1355,14 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         const int LB = 1 << g.lshift_x;
         dim3 grid((g.P[1] + LB - 1) / LB, g.P[2], 1);
         bs_launch_scope sc(ctx, "fft_x_c2r");
-        if (g.static_x && g.lshift_x == 3) k_fft_x_c2r<FftX270L8><<<grid, PCM_THREADS, g.smem_x_c2r, ctx->stream>>>(a);
+        const size_t smem_w = ((size_t)g.P[0] + (size_t)(PCM_THREADS / 32) * 2 * (g.M + 1)) * sizeof(float2);
+        if (env_int("BS_FFT_X_WARP", 1) && g.M <= 32 * XW_MAXV - 1 && smem_w <= PCM_SMEM_MAX) {
+            const long long n_lines = (long long)g.P[1] * g.P[2];
+            const int per_sm = std::max(1, std::min(6, (int)(PCM_SMEM_MAX / (smem_w + 1024))));
+            const int nctas = (int)std::min<long long>((n_lines + 7) / 8, (long long)ctx->sm_count * per_sm);
+            if (g.M == FftW270::N && env_int("BS_FFT_STATIC", 1)) k_fft_x_c2r_w<FftW270><<<nctas, PCM_THREADS, smem_w, ctx->stream>>>(a);
+            else k_fft_x_c2r_w<FftWGeneric><<<nctas, PCM_THREADS, smem_w, ctx->stream>>>(a);
+        } else if (g.static_x && g.lshift_x == 3) k_fft_x_c2r<FftX270L8><<<grid, PCM_THREADS, g.smem_x_c2r, ctx->stream>>>(a);
         else if (g.static_x) k_fft_x_c2r<FftX270><<<grid, PCM_THREADS, g.smem_x_c2r, ctx->stream>>>(a);
         else k_fft_x_c2r<FftGeneric><<<grid, PCM_THREADS, g.smem_x_c2r, ctx->stream>>>(a);
     }
@@ -1093,11 +1562,11 @@ static int pcm_run(bs_ctx* ctx, const void* d1, const void* d2, const long long 
         a.sums_u = (unsigned long long*)(dsmall + off_sums);
         a.sums_d = (double*)(dsmall + off_sums);
         const long long rows = (long long)g.d[1] * g.d[2];
-        const int ctas = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, (long long)ctx->sm_count * 8));
-        dim3 grid(ctas, nslots, 1);
+        const long long chunks = (rows + PR_ROWS - 1) / PR_ROWS;
+        const int ctas = (int)std::max<long long>(1, std::min<long long>((chunks + 7) / 8, (long long)ctx->sm_count * 8));
         {
             bs_launch_scope sc(ctx, "pearson");
-            k_pearson<<<grid, PCM_THREADS, 0, ctx->stream>>>(a);
+            k_pearson<<<ctas, PCM_THREADS, sizeof(unsigned long long) * 5 * nslots, ctx->stream>>>(a, nslots);
         }
         BS_CUDA(ctx, cudaGetLastError());
         BS_CUDA(ctx, cudaMemcpyAsync(hsums, dsmall + off_sums, sizeof(unsigned long long) * 5 * nslots, cudaMemcpyDeviceToHost, ctx->stream));

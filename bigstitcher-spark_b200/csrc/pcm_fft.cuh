@@ -300,3 +300,109 @@ struct FftStatic {
         return fft_tile_s<N_, 1, LSHIFT_, LSTRIDE_, TWMUL_, NT_, Rs...>(a, b, tw);
     }
 };
+
+
+// ------------------------------------------------------------------------------------------
+// Warp-private line FFT: ONE warp transforms ONE contiguous line (buf[e]) with only
+// __syncwarp() between stages, so the x passes need no block-wide barriers at all and the 8
+// warps of a CTA drift freely (one warp's loads overlap another's butterflies).
+template <int R>
+__device__ __forceinline__ void fft_stage_wg(const float2* __restrict__ in, float2* __restrict__ out,
+                                             const float2* __restrict__ tw, int N, int Ls, int twmul, int lane) {
+    const int m = N / R;
+    const int twstep = (N / (Ls * R)) * twmul;
+    for (int j = lane; j < m; j += 32) {
+        const int k = (Ls == 1) ? 0 : (j % Ls);
+        float2 x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = in[j + q * m];
+        if (Ls > 1) {
+            const int ts = k * twstep;
+#pragma unroll
+            for (int q = 1; q < R; ++q) x[q] = cmulf(x[q], tw[q * ts]);
+        }
+        dft<R>(x);
+        float2* o = out + (j - k) * R + k;
+#pragma unroll
+        for (int q = 0; q < R; ++q) o[q * Ls] = x[q];
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ float2* fft_line_wg(float2* a, float2* b, const float2* tw, const FftPlan& plan, int twmul,
+                                               int lane) {
+    int Ls = 1;
+    const int N = plan.n;
+    for (int s = 0; s < plan.nst; ++s) {
+        const int r = plan.radix[s];
+        switch (r) {
+            case 2: fft_stage_wg<2>(a, b, tw, N, Ls, twmul, lane); break;
+            case 3: fft_stage_wg<3>(a, b, tw, N, Ls, twmul, lane); break;
+            case 4: fft_stage_wg<4>(a, b, tw, N, Ls, twmul, lane); break;
+            case 5: fft_stage_wg<5>(a, b, tw, N, Ls, twmul, lane); break;
+            case 6: fft_stage_wg<6>(a, b, tw, N, Ls, twmul, lane); break;
+            case 8: fft_stage_wg<8>(a, b, tw, N, Ls, twmul, lane); break;
+            case 9: fft_stage_wg<9>(a, b, tw, N, Ls, twmul, lane); break;
+            case 10: fft_stage_wg<10>(a, b, tw, N, Ls, twmul, lane); break;
+            case 12: fft_stage_wg<12>(a, b, tw, N, Ls, twmul, lane); break;
+            case 15: fft_stage_wg<15>(a, b, tw, N, Ls, twmul, lane); break;
+            case 16: fft_stage_wg<16>(a, b, tw, N, Ls, twmul, lane); break;
+            default: break;
+        }
+        Ls *= r;
+        float2* t = a; a = b; b = t;
+    }
+    return a;
+}
+
+template <int N, int R, int LS, int TWMUL>
+__device__ __forceinline__ void fft_stage_ws(const float2* __restrict__ in, float2* __restrict__ out,
+                                             const float2* __restrict__ tw, int lane) {
+    constexpr int m = N / R;
+    constexpr int twstep = (N / (LS * R)) * TWMUL;
+    constexpr int iters = (m + 31) / 32;
+#pragma unroll
+    for (int it = 0; it < iters; ++it) {
+        const int j = lane + 32 * it;
+        if ((m % 32) != 0 && it == iters - 1 && j >= m) break;
+        const int k = (LS == 1) ? 0 : (j % LS);
+        float2 x[R];
+#pragma unroll
+        for (int q = 0; q < R; ++q) x[q] = in[j + q * m];
+        if (LS > 1) {
+            const int ts = k * twstep;
+#pragma unroll
+            for (int q = 1; q < R; ++q) x[q] = cmulf(x[q], tw[q * ts]);
+        }
+        dft<R>(x);
+        float2* o = out + (j - k) * R + k;
+#pragma unroll
+        for (int q = 0; q < R; ++q) o[q * LS] = x[q];
+    }
+    __syncwarp();
+}
+
+template <int N, int LS, int TWMUL, int R, int... Rest>
+__device__ __forceinline__ float2* fft_line_ws(float2* a, float2* b, const float2* tw, int lane) {
+    fft_stage_ws<N, R, LS, TWMUL>(a, b, tw, lane);
+    if constexpr (sizeof...(Rest) == 0) return b;
+    else return fft_line_ws<N, LS * R, TWMUL, Rest...>(b, a, tw, lane);
+}
+
+struct FftWGeneric {
+    static constexpr bool kStatic = false;
+    static constexpr int N = 0;
+    static __device__ __forceinline__ float2* run(float2* a, float2* b, const float2* tw, const FftPlan& plan,
+                                                  int twmul, int lane) {
+        return fft_line_wg(a, b, tw, plan, twmul, lane);
+    }
+};
+
+template <int N_, int TWMUL_, int... Rs>
+struct FftWStatic {
+    static constexpr bool kStatic = true;
+    static constexpr int N = N_;
+    static __device__ __forceinline__ float2* run(float2* a, float2* b, const float2* tw, const FftPlan&, int, int lane) {
+        return fft_line_ws<N_, 1, TWMUL_, Rs...>(a, b, tw, lane);
+    }
+};
