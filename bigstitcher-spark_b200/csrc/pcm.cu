@@ -440,35 +440,51 @@ __global__ void __launch_bounds__(PCM_THREADS) k_fft_x_r2c_w(const __grid_consta
         } else {
             rrow = reinterpret_cast<const unsigned char*>(a.img[im]) + (size_t)row * t.row_bytes;  // global
         }
-        for (int n = lane; n < M; n += 32) {
-            float2 v = make_float2(0.f, 0.f);
-            const int xp = 2 * n;
-            if (xp >= e0 && xp + 1 < e0 + a.dx) {
-                v = make_float2(raw_elem(rrow, a.dtype, xp - e0) * gyz, raw_elem(rrow, a.dtype, xp - e0 + 1) * gyz);
-            } else if (xp < a.Ex) {
-                const float g0 = (a.w_x[xp] * wy) * wz, g1 = (a.w_x[xp + 1] * wy) * wz;
-                const float p0 = raw_elem(rrow, a.dtype, a.idx_x[xp]), p1 = raw_elem(rrow, a.dtype, a.idx_x[xp + 1]);
-                v = make_float2(g0 != 0.f ? p0 * g0 : 0.f, g1 != 0.f ? p1 * g1 : 0.f);
+        if (a.dtype == BS_DTYPE_U16 && !(e0 & 1) && !((size_t)rrow & 3)) {
+            // interior pairs are aligned 32-bit words of the staged row
+            const unsigned int* r32 = reinterpret_cast<const unsigned int*>(rrow);
+            const int n_lo = e0 >> 1, n_hi = (e0 + a.dx) >> 1;   // pairs fully inside [e0, e0 + dx)
+            for (int n = lane; n < M; n += 32) {
+                float2 v = make_float2(0.f, 0.f);
+                if (n >= n_lo && n < n_hi) {
+                    const unsigned int w = r32[n - n_lo];
+                    v = make_float2((float)(w & 0xffffu) * gyz, (float)(w >> 16) * gyz);
+                } else if (2 * n < a.Ex) {
+                    const int xp = 2 * n;
+                    const float g0 = (a.w_x[xp] * wy) * wz, g1 = (a.w_x[xp + 1] * wy) * wz;
+                    const float p0 = raw_elem(rrow, BS_DTYPE_U16, a.idx_x[xp]), p1 = raw_elem(rrow, BS_DTYPE_U16, a.idx_x[xp + 1]);
+                    v = make_float2(g0 != 0.f ? p0 * g0 : 0.f, g1 != 0.f ? p1 * g1 : 0.f);
+                }
+                A[n] = v;
             }
-            A[n] = v;
+        } else {
+            for (int n = lane; n < M; n += 32) {
+                float2 v = make_float2(0.f, 0.f);
+                const int xp = 2 * n;
+                if (xp >= e0 && xp + 1 < e0 + a.dx) {
+                    v = make_float2(raw_elem(rrow, a.dtype, xp - e0) * gyz, raw_elem(rrow, a.dtype, xp - e0 + 1) * gyz);
+                } else if (xp < a.Ex) {
+                    const float g0 = (a.w_x[xp] * wy) * wz, g1 = (a.w_x[xp + 1] * wy) * wz;
+                    const float p0 = raw_elem(rrow, a.dtype, a.idx_x[xp]), p1 = raw_elem(rrow, a.dtype, a.idx_x[xp + 1]);
+                    v = make_float2(g0 != 0.f ? p0 * g0 : 0.f, g1 != 0.f ? p1 * g1 : 0.f);
+                }
+                A[n] = v;
+            }
         }
         __syncwarp();
         const float2* res = F::run(A, B, tw, a.plan, 2, lane);
-        for (int k = lane; k < pitch; k += 32) {
-            float2 X = make_float2(0.f, 0.f);
-            if (k <= M) {
-                const int k0 = (k == M) ? 0 : k;
-                const int k1 = (k == 0 || k == M) ? 0 : M - k;
-                const float2 Zk = res[k0];
-                float2 Zm = res[k1];
-                Zm.y = -Zm.y;
-                const float2 E = make_float2(0.5f * (Zk.x + Zm.x), 0.5f * (Zk.y + Zm.y));
-                const float2 D = make_float2(0.5f * (Zk.x - Zm.x), 0.5f * (Zk.y - Zm.y));
-                const float2 wD = cmulf(tw[k], D);
-                X = make_float2(E.x + wD.y, E.y - wD.x);
-            }
-            __stcg(srow + k, X);
+        // untangle: X[k] and X[M-k] share E, D and the twiddle (w_{M-k} = -conj(w_k))
+        for (int k = lane; 2 * k <= M; k += 32) {
+            const float2 Zk = res[k];
+            float2 Zm = res[k == 0 ? 0 : M - k];
+            Zm.y = -Zm.y;
+            const float2 E = make_float2(0.5f * (Zk.x + Zm.x), 0.5f * (Zk.y + Zm.y));
+            const float2 D = make_float2(0.5f * (Zk.x - Zm.x), 0.5f * (Zk.y - Zm.y));
+            const float2 wD = cmulf(tw[k], D);
+            __stcg(srow + k, make_float2(E.x + wD.y, E.y - wD.x));            // E - i w D
+            if (2 * k != M) __stcg(srow + (M - k), make_float2(E.x - wD.y, -E.y - wD.x));   // conj(E) - i conj(w D)
         }
+        for (int k = M + 1 + lane; k < pitch; k += 32) __stcg(srow + k, make_float2(0.f, 0.f));
         __syncwarp();  // A/B and the consumed raw buffer are free again
     }
 }
@@ -857,9 +873,9 @@ __device__ __forceinline__ void pr_acc(unsigned int va, unsigned int vb, unsigne
                                        unsigned long long& saa, unsigned long long& sbb, unsigned long long& sab) {
     ra += va;
     rb += vb;
-    saa += (unsigned long long)(va * va);
-    sbb += (unsigned long long)(vb * vb);
-    sab += (unsigned long long)(va * vb);
+    saa += (unsigned long long)va * va;   // one IMAD.WIDE.U32 with 64-bit accumulate each
+    sbb += (unsigned long long)vb * vb;
+    sab += (unsigned long long)va * vb;
 }
 
 __device__ __forceinline__ void pearson_u16(const PearsonArgs& a, int ncand, unsigned long long* s_acc) {
@@ -902,19 +918,23 @@ __device__ __forceinline__ void pearson_u16(const PearsonArgs& a, int ncand, uns
                 } else if (even_rows && n >= 4) {
                     // exactly one x offset is odd: aligned words on one side, funnel-shifted pairs of
                     // aligned words on the other (element -1 and the following words stay inside the row)
+                    // the aligned side is accumulated as "a", the funnel-shifted side as "b"; the
+                    // a/b statistics are swapped once per row when image 1 is the shifted side
                     const bool odd1 = cd.o1[0] & 1;
                     const unsigned int* qa = reinterpret_cast<const unsigned int*>(odd1 ? p2 : p1);
                     const unsigned int* qm = reinterpret_cast<const unsigned int*>((odd1 ? p1 : p2) - 1);
                     const int nv = (n >> 1) - 1;  // last pair(s) handled below: qm[x + 1] must not leave the row
+                    unsigned int ta = 0, tb = 0;
+                    unsigned long long taa = 0, tbb = 0;
 #pragma unroll 4
                     for (int x = lane; x < nv; x += 32) {
                         const unsigned int wa = __ldg(qa + x);
                         const unsigned int wm = __funnelshift_r(__ldg(qm + x), __ldg(qm + x + 1), 16);
-                        const unsigned int a0 = odd1 ? (wm & 0xffffu) : (wa & 0xffffu), a1 = odd1 ? (wm >> 16) : (wa >> 16);
-                        const unsigned int b0 = odd1 ? (wa & 0xffffu) : (wm & 0xffffu), b1 = odd1 ? (wa >> 16) : (wm >> 16);
-                        pr_acc(a0, b0, ra, rb, saa, sbb, sab);
-                        pr_acc(a1, b1, ra, rb, saa, sbb, sab);
+                        pr_acc(wa & 0xffffu, wm & 0xffffu, ta, tb, taa, tbb, sab);
+                        pr_acc(wa >> 16, wm >> 16, ta, tb, taa, tbb, sab);
                     }
+                    if (odd1) { ra += tb; rb += ta; saa += tbb; sbb += taa; }
+                    else { ra += ta; rb += tb; saa += taa; sbb += tbb; }
                     for (int x = 2 * nv + lane; x < n; x += 32) pr_acc(__ldg(p1 + x), __ldg(p2 + x), ra, rb, saa, sbb, sab);
                 } else {
 #pragma unroll 4
