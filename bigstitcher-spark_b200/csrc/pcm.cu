@@ -868,6 +868,7 @@ struct PearsonArgs {
 // candidate on them before moving on, so all candidates stream through the volumes in lockstep and
 // the second..K-th read of a row is an L1/L2 hit (DRAM traffic ~ one sweep instead of K sweeps).
 #define PR_ROWS 8
+#define PR_MLP 8
 
 __device__ __forceinline__ void pr_acc(unsigned int va, unsigned int vb, unsigned int& ra, unsigned int& rb,
                                        unsigned long long& saa, unsigned long long& sbb, unsigned long long& sab) {
@@ -908,11 +909,19 @@ __device__ __forceinline__ void pearson_u16(const PearsonArgs& a, int ncand, uns
                     const unsigned int* q1 = reinterpret_cast<const unsigned int*>(p1);
                     const unsigned int* q2 = reinterpret_cast<const unsigned int*>(p2);
                     const int nv = n >> 1;
-#pragma unroll 4
-                    for (int x = lane; x < nv; x += 32) {
-                        const unsigned int w1 = __ldg(q1 + x), w2 = __ldg(q2 + x);
-                        pr_acc(w1 & 0xffffu, w2 & 0xffffu, ra, rb, saa, sbb, sab);
-                        pr_acc(w1 >> 16, w2 >> 16, ra, rb, saa, sbb, sab);
+                    for (int x0 = lane; x0 < nv; x0 += 32 * PR_MLP) {   // PR_MLP words per image in flight per lane
+                        unsigned int w1[PR_MLP], w2[PR_MLP];
+#pragma unroll
+                        for (int u = 0; u < PR_MLP; ++u) {
+                            const int x = x0 + 32 * u;
+                            w1[u] = x < nv ? __ldg(q1 + x) : 0u;
+                            w2[u] = x < nv ? __ldg(q2 + x) : 0u;
+                        }
+#pragma unroll
+                        for (int u = 0; u < PR_MLP; ++u) {
+                            pr_acc(w1[u] & 0xffffu, w2[u] & 0xffffu, ra, rb, saa, sbb, sab);
+                            pr_acc(w1[u] >> 16, w2[u] >> 16, ra, rb, saa, sbb, sab);
+                        }
                     }
                     if ((n & 1) && lane == 0) pr_acc(__ldg(p1 + n - 1), __ldg(p2 + n - 1), ra, rb, saa, sbb, sab);
                 } else if (even_rows && n >= 4) {
@@ -926,12 +935,21 @@ __device__ __forceinline__ void pearson_u16(const PearsonArgs& a, int ncand, uns
                     const int nv = (n >> 1) - 1;  // last pair(s) handled below: qm[x + 1] must not leave the row
                     unsigned int ta = 0, tb = 0;
                     unsigned long long taa = 0, tbb = 0;
-#pragma unroll 4
-                    for (int x = lane; x < nv; x += 32) {
-                        const unsigned int wa = __ldg(qa + x);
-                        const unsigned int wm = __funnelshift_r(__ldg(qm + x), __ldg(qm + x + 1), 16);
-                        pr_acc(wa & 0xffffu, wm & 0xffffu, ta, tb, taa, tbb, sab);
-                        pr_acc(wa >> 16, wm >> 16, ta, tb, taa, tbb, sab);
+                    for (int x0 = lane; x0 < nv; x0 += 32 * PR_MLP) {
+                        unsigned int wa[PR_MLP], m0[PR_MLP], m1[PR_MLP];
+#pragma unroll
+                        for (int u = 0; u < PR_MLP; ++u) {
+                            const int x = x0 + 32 * u;
+                            wa[u] = x < nv ? __ldg(qa + x) : 0u;
+                            m0[u] = x < nv ? __ldg(qm + x) : 0u;
+                            m1[u] = x < nv ? __ldg(qm + x + 1) : 0u;
+                        }
+#pragma unroll
+                        for (int u = 0; u < PR_MLP; ++u) {
+                            const unsigned int wm = __funnelshift_r(m0[u], m1[u], 16);
+                            pr_acc(wa[u] & 0xffffu, wm & 0xffffu, ta, tb, taa, tbb, sab);
+                            pr_acc(wa[u] >> 16, wm >> 16, ta, tb, taa, tbb, sab);
+                        }
                     }
                     if (odd1) { ra += tb; rb += ta; saa += tbb; sbb += taa; }
                     else { ra += ta; rb += tb; saa += taa; sbb += tbb; }
