@@ -1,0 +1,223 @@
+"""Minimal N5 reader / writer for the data formats either side of the hot path (SURVEY.md 8f-1,
+Appendix B; n5 3.5.0, pom.xml:109-111).
+
+Covers what `stitching` / `affine-fusion` touch: dataset `attributes.json`, block files
+`<dataset>/<gx>/<gy>/<gz>` with the big-endian header (uint16 mode, uint16 ndim, ndim x uint32
+block dims) followed by big-endian x-fastest elements, `raw` and `gzip` compression (zstd, the
+reference's default, is not available in this image: J/CreateFusionContainer.java:71-76), the BDV-N5
+input layout `setup{S}/timepoint{T}/s{L}` and the container root attributes `Bigstitcher-Spark/*`
+(J/CreateFusionContainer.java:302-320,519; read back at J/SparkAffineFusion.java:241-307).
+Host-side plumbing only -- no voxel arithmetic.
+"""
+from __future__ import annotations
+
+import gzip
+import json
+import os
+import struct
+import zlib
+
+import numpy as np
+
+_DTYPES = {"uint8": np.uint8, "uint16": np.uint16, "uint32": np.uint32, "int16": np.int16,
+           "float32": np.float32, "float64": np.float64}
+
+
+def _dtype_name(dt):
+    dt = np.dtype(dt)
+    for k, v in _DTYPES.items():
+        if np.dtype(v) == dt:
+            return k
+    raise ValueError(f"unsupported dtype {dt}")
+
+
+class N5Store:
+    """Filesystem N5 container."""
+
+    def __init__(self, root: str, create: bool = False):
+        self.root = root
+        if create:
+            os.makedirs(root, exist_ok=True)
+            if not os.path.exists(os.path.join(root, "attributes.json")):
+                self.set_attributes("", {"n5": "2.5.1"})
+        elif not os.path.isdir(root):
+            raise FileNotFoundError(root)
+
+    # -- attributes
+    def _attr_path(self, group):
+        return os.path.join(self.root, group.strip("/"), "attributes.json")
+
+    def get_attributes(self, group=""):
+        p = self._attr_path(group)
+        if not os.path.exists(p):
+            return {}
+        with open(p) as f:
+            return json.load(f)
+
+    def set_attributes(self, group, attrs: dict):
+        p = self._attr_path(group)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        cur = self.get_attributes(group)
+        cur.update(attrs)
+        with open(p, "w") as f:
+            json.dump(cur, f)
+
+    # -- datasets
+    def create_dataset(self, path, dimensions, block_size, dtype, compression="raw"):
+        comp = {"type": compression}
+        if compression == "gzip":
+            comp["level"] = 1  # reference default, J/util/N5Util.java:82-105
+        self.set_attributes(path, {"dimensions": [int(d) for d in dimensions],
+                                   "blockSize": [int(b) for b in block_size],
+                                   "dataType": _dtype_name(dtype), "compression": comp})
+
+    def dataset_attributes(self, path):
+        a = self.get_attributes(path)
+        if "dimensions" not in a:
+            raise KeyError(f"{path} is not an N5 dataset")
+        return a
+
+    def _block_path(self, path, grid_pos):
+        return os.path.join(self.root, path.strip("/"), *[str(int(g)) for g in grid_pos])
+
+    def write_block(self, path, grid_pos, block: np.ndarray):
+        """block: [z, y, x] array (x fastest), at most blockSize in every dimension."""
+        a = self.dataset_attributes(path)
+        dt = np.dtype(_DTYPES[a["dataType"]])
+        if block.dtype != dt:
+            raise ValueError(f"block dtype {block.dtype} != dataset dtype {dt}")
+        dims_xyz = block.shape[::-1]
+        header = struct.pack(">HH", 0, len(dims_xyz)) + b"".join(struct.pack(">I", int(d)) for d in dims_xyz)
+        payload = np.ascontiguousarray(block).astype(dt.newbyteorder(">"), copy=False).tobytes()
+        ctype = a["compression"]["type"]
+        if ctype == "gzip":
+            payload = gzip.compress(payload, compresslevel=a["compression"].get("level", 1))
+        elif ctype != "raw":
+            raise NotImplementedError(f"compression {ctype} (not available in this image)")
+        p = self._block_path(path, grid_pos)
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        with open(p, "wb") as f:
+            f.write(header + payload)
+
+    def read_block(self, path, grid_pos):
+        """Returns the [z, y, x] block or None when the block file does not exist."""
+        a = self.dataset_attributes(path)
+        p = self._block_path(path, grid_pos)
+        if not os.path.exists(p):
+            return None
+        with open(p, "rb") as f:
+            buf = f.read()
+        mode, ndim = struct.unpack(">HH", buf[:4])
+        if mode != 0:
+            raise NotImplementedError("varlength / object N5 blocks")
+        dims = struct.unpack(">" + "I" * ndim, buf[4:4 + 4 * ndim])
+        payload = buf[4 + 4 * ndim:]
+        ctype = a["compression"]["type"]
+        if ctype == "gzip":
+            payload = zlib.decompress(payload, 16 + zlib.MAX_WBITS)
+        elif ctype != "raw":
+            raise NotImplementedError(f"compression {ctype}")
+        dt = np.dtype(_DTYPES[a["dataType"]])
+        arr = np.frombuffer(payload, dtype=dt.newbyteorder(">"), count=int(np.prod(dims)))
+        return arr.astype(dt).reshape(dims[::-1])
+
+    def read_volume(self, path):
+        """Whole dataset as a [z, y, x] array (missing blocks are zero)."""
+        a = self.dataset_attributes(path)
+        dims = a["dimensions"]
+        bs = a["blockSize"]
+        out = np.zeros(dims[::-1], dtype=_DTYPES[a["dataType"]])
+        grid = [int(np.ceil(dims[d] / bs[d])) for d in range(3)]
+        for gz in range(grid[2]):
+            for gy in range(grid[1]):
+                for gx in range(grid[0]):
+                    b = self.read_block(path, (gx, gy, gz))
+                    if b is None:
+                        continue
+                    z, y, x = b.shape
+                    out[gz * bs[2]:gz * bs[2] + z, gy * bs[1]:gy * bs[1] + y, gx * bs[0]:gx * bs[0] + x] = b
+        return out
+
+    def save_block(self, path, volume: np.ndarray, grid_offset):
+        """N5Utils.saveBlock(img, writer, dataset, gridOffset) (J/SparkAffineFusion.java:670): split
+        a super-block into storage blocks starting at grid position ``grid_offset`` and write them."""
+        a = self.dataset_attributes(path)
+        bs = a["blockSize"]
+        dims = a["dimensions"]
+        sz = volume.shape[::-1]
+        n = [int(np.ceil(sz[d] / bs[d])) for d in range(3)]
+        for kz in range(n[2]):
+            for ky in range(n[1]):
+                for kx in range(n[0]):
+                    g = (grid_offset[0] + kx, grid_offset[1] + ky, grid_offset[2] + kz)
+                    if any(g[d] * bs[d] >= dims[d] for d in range(3)):
+                        continue
+                    blk = volume[kz * bs[2]:(kz + 1) * bs[2], ky * bs[1]:(ky + 1) * bs[1], kx * bs[0]:(kx + 1) * bs[0]]
+                    self.write_block(path, g, blk)
+
+    def write_volume(self, path, volume: np.ndarray, block_size, compression="raw"):
+        self.create_dataset(path, volume.shape[::-1], block_size, volume.dtype, compression)
+        self.save_block(path, volume, (0, 0, 0))
+
+
+# ---------------------------------------------------------------------------------------------
+# BDV-N5 input layout and the fusion-container contract
+def bdv_dataset(setup: int, timepoint: int, level: int = 0) -> str:
+    """`setup{S}/timepoint{T}/s{L}` (J/util/Import.java:319-326)."""
+    return f"setup{setup}/timepoint{timepoint}/s{level}"
+
+
+def write_bdv_setup(store: N5Store, setup: int, timepoint: int, volume: np.ndarray, block_size=(128, 128, 128),
+                    downsampling_factors=((1, 1, 1),), compression="raw"):
+    store.set_attributes(f"setup{setup}", {"downsamplingFactors": [list(f) for f in downsampling_factors],
+                                           "dataType": _dtype_name(volume.dtype)})
+    store.set_attributes(f"setup{setup}/timepoint{timepoint}", {"resolution": [1.0, 1.0, 1.0], "multiScale": True})
+    store.write_volume(bdv_dataset(setup, timepoint, 0), volume, block_size, compression)
+
+
+def create_fusion_container(root, input_xml, bb_min, bb_max, block_size=(128, 128, 128), dtype="float32",
+                            min_intensity=None, max_intensity=None, num_timepoints=1, num_channels=1,
+                            anisotropy_factor=None, compression="raw"):
+    """`create-fusion-container -s N5` (J/CreateFusionContainer.java:302-320,490-519): per
+    (channel, timepoint) dataset `ch{c}tp{t}/s0` plus the `Bigstitcher-Spark/*` root attributes
+    that `affine-fusion` reads back (J/SparkAffineFusion.java:241-307)."""
+    store = N5Store(root, create=True)
+    dims = [int(bb_max[d] - bb_min[d] + 1) for d in range(3)]
+    mr = []
+    for t in range(num_timepoints):
+        for c in range(num_channels):
+            ds = f"ch{c}tp{t}/s0"
+            store.create_dataset(ds, dims, block_size, _DTYPES[dtype], compression)
+            mr.append([{"dataset": ds, "dimensions": dims, "blockSize": list(block_size),
+                        "relativeDownsampling": [1, 1, 1], "absoluteDownsampling": [1, 1, 1], "dataType": dtype}])
+    attrs = {"Bigstitcher-Spark/FusionFormat": "N5", "Bigstitcher-Spark/InputXML": input_xml,
+             "Bigstitcher-Spark/NumTimepoints": num_timepoints, "Bigstitcher-Spark/NumChannels": num_channels,
+             "Bigstitcher-Spark/Boundingbox_min": [int(v) for v in bb_min],
+             "Bigstitcher-Spark/Boundingbox_max": [int(v) for v in bb_max],
+             "Bigstitcher-Spark/PreserveAnisotropy": anisotropy_factor is not None,
+             "Bigstitcher-Spark/DataType": dtype.upper(), "Bigstitcher-Spark/BlockSize": list(block_size),
+             "Bigstitcher-Spark/MultiResolutionInfos": mr}
+    if anisotropy_factor is not None:
+        attrs["Bigstitcher-Spark/AnisotropyFactor"] = float(anisotropy_factor)
+    if dtype != "float32":
+        attrs["Bigstitcher-Spark/MinIntensity"] = float(min_intensity)
+        attrs["Bigstitcher-Spark/MaxIntensity"] = float(max_intensity)
+    store.set_attributes("", attrs)
+    return store
+
+
+def read_fusion_container(root):
+    """The metadata `affine-fusion` needs (J/SparkAffineFusion.java:241-307)."""
+    store = N5Store(root)
+    a = store.get_attributes("")
+    g = lambda k, d=None: a.get("Bigstitcher-Spark/" + k, d)  # noqa: E731
+    if g("FusionFormat") is None:
+        raise KeyError("not a BigStitcher-Spark fusion container (no Bigstitcher-Spark/FusionFormat)")
+    return store, {
+        "format": g("FusionFormat"), "input_xml": g("InputXML"), "num_timepoints": g("NumTimepoints", 1),
+        "num_channels": g("NumChannels", 1), "bb_min": g("Boundingbox_min"), "bb_max": g("Boundingbox_max"),
+        "preserve_anisotropy": g("PreserveAnisotropy", False), "anisotropy_factor": g("AnisotropyFactor", float("nan")),
+        "dtype": g("DataType", "FLOAT32").lower(), "block_size": g("BlockSize"),
+        "min_intensity": g("MinIntensity", 0.0), "max_intensity": g("MaxIntensity", 65535.0),
+        "mr_infos": g("MultiResolutionInfos"),
+    }

@@ -1,0 +1,220 @@
+"""Minimal SpimData2 XML reader / writer (spim_data 2.3.5 + mvrecon
+extensions) -- the fields the two hot paths consume and produce:
+
+  * ViewSetups: id, size, attributes (illumination / channel / tile / angle)   (J/util/ViewUtil.java:107-109,
+    grouping at J/SparkPairwiseStitching.java:147-160)
+  * ViewRegistrations: ordered <ViewTransform type="affine"> lists; list index 0 is applied LAST
+    (J/ClearRegistrations.java:80-99), so model = T0 * T1 * ... * Tn
+  * ImageLoader format="bdv.n5" path (J/SparkResaveN5.java:424-433)
+  * <StitchingResults><PairwiseResult view_setup_a/b tp_a/b> shift (12 doubles), correlation, hash,
+    overlap_boundingbox (6 doubles)                                   (J/SparkPairwiseStitching.java:284-301,328-390)
+
+Host-side plumbing only.  Everything else in the file is preserved verbatim on save.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import xml.etree.ElementTree as ET
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class ViewSetup:
+    id: int
+    size: tuple                      # (x, y, z)
+    attributes: dict = field(default_factory=dict)   # illumination / channel / tile / angle -> int
+
+
+def _fmt(values):
+    return " ".join(repr(float(v)) for v in values)
+
+
+class SpimData2:
+    def __init__(self, tree: ET.ElementTree, path: str | None = None):
+        self.tree = tree
+        self.root = tree.getroot()
+        self.path = path
+        self.setups: dict[int, ViewSetup] = {}
+        self.registrations: dict[tuple, list] = {}   # (tp, setup) -> [(name, 3x4 ndarray)], index 0 applied last
+        self.timepoints: list[int] = []
+        self._parse()
+
+    # ------------------------------------------------------------------ load / save
+    @classmethod
+    def load(cls, path: str) -> "SpimData2":
+        return cls(ET.parse(path), path)
+
+    def _parse(self):
+        seq = self.root.find("SequenceDescription")
+        for vs in seq.find("ViewSetups").findall("ViewSetup"):
+            sid = int(vs.findtext("id"))
+            size = tuple(int(v) for v in vs.findtext("size").split())
+            attrs = {}
+            a = vs.find("attributes")
+            if a is not None:
+                for ch in a:
+                    attrs[ch.tag] = int(ch.text)
+            self.setups[sid] = ViewSetup(sid, size, attrs)
+        tps = set()
+        for vr in self.root.find("ViewRegistrations").findall("ViewRegistration"):
+            tp, setup = int(vr.get("timepoint")), int(vr.get("setup"))
+            lst = []
+            for vt in vr.findall("ViewTransform"):
+                m = np.array([float(v) for v in vt.findtext("affine").split()], dtype=np.float64).reshape(3, 4)
+                lst.append((vt.findtext("Name") or "", m))
+            self.registrations[(tp, setup)] = lst
+            tps.add(tp)
+        self.timepoints = sorted(tps)
+
+    def image_loader(self):
+        """(format, absolute container path) of the ImageLoader element."""
+        il = self.root.find("SequenceDescription").find("ImageLoader")
+        fmt = il.get("format")
+        node = il.find("n5") if il.find("n5") is not None else (il.find("zarr") if il.find("zarr") is not None else il.find("hdf5"))
+        p = node.text.strip() if node is not None else None
+        if p is not None and node.get("type", "relative") == "relative" and self.path:
+            base = self.root.findtext("BasePath") or "."
+            p = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(self.path)), base, p))
+        return fmt, p
+
+    def save(self, path: str | None = None, backup: bool = True):
+        path = path or self.path
+        if backup and os.path.exists(path):
+            shutil.copyfile(path, path + "~1")   # the reference keeps ~1 backups (J/SparkResaveN5.java:80)
+        ET.indent(self.tree, space="  ")
+        self.tree.write(path, encoding="UTF-8", xml_declaration=True)
+
+    # ------------------------------------------------------------------ registrations
+    def model(self, tp: int, setup: int) -> np.ndarray:
+        """ViewRegistration.getModel(): concatenation of the transform list, index 0 applied last."""
+        M = np.eye(4)
+        for _, m in self.registrations[(tp, setup)]:
+            M = M @ np.vstack([m, [0, 0, 0, 1]])
+        return M[:3, :].copy()
+
+    def view_ids(self):
+        return sorted(self.registrations)
+
+    # ------------------------------------------------------------------ pair construction (row a1)
+    def stitching_pairs(self):
+        """All tile pairs per (timepoint, angle, channel, illumination) whose transformed bounding
+        boxes overlap (SpimDataFilteringAndGrouping + filterNonOverlappingPairs,
+        J/SparkPairwiseStitching.java:142-176).  Single-view groups (one channel / illumination)."""
+        pairs = []
+        vids = self.view_ids()
+        boxes = {}
+        for (tp, s) in vids:
+            M = self.model(tp, s)
+            dx, dy, dz = self.setups[s].size
+            c = np.array([[x, y, z] for x in (0, dx - 1) for y in (0, dy - 1) for z in (0, dz - 1)], dtype=np.float64)
+            w = c @ M[:, :3].T + M[:, 3]
+            boxes[(tp, s)] = (w.min(axis=0), w.max(axis=0))
+        for i, a in enumerate(vids):
+            for b in vids[i + 1:]:
+                if a[0] != b[0]:
+                    continue
+                sa, sb = self.setups[a[1]].attributes, self.setups[b[1]].attributes
+                if any(sa.get(k, 0) != sb.get(k, 0) for k in ("angle", "channel", "illumination")):
+                    continue
+                if sa.get("tile", a[1]) == sb.get("tile", b[1]):
+                    continue
+                lo = np.maximum(boxes[a][0], boxes[b][0])
+                hi = np.minimum(boxes[a][1], boxes[b][1])
+                if np.all(hi >= lo):
+                    pairs.append((a, b))
+        return pairs
+
+    # ------------------------------------------------------------------ stitching results (rows a6, f-2)
+    @staticmethod
+    def transform_hash(reg_a, reg_b) -> float:
+        """Stand-in for PairwiseStitchingResult.calculateHash(vrA, vrB): a double derived from both
+        views' transform coefficients.  Upstream's exact formula is not recoverable here (PARITY_GAPS
+        #22); the Java glue recomputes it with the real method (J/SparkPairwiseStitching.java:287-289),
+        `solver` only tests it for equality (J/Solver.java:407-414)."""
+        h = 0.0
+        for lst in (reg_a, reg_b):
+            for i, (_, m) in enumerate(lst):
+                h += float(np.sum(m * (np.arange(12).reshape(3, 4) + 1 + 13 * i)))
+        return h
+
+    def stitching_results(self):
+        out = []
+        sr = self.root.find("StitchingResults")
+        if sr is None:
+            return out
+        for pr in sr.findall("PairwiseResult"):
+            a = (int(pr.get("tp_a")), int(pr.get("view_setup_a")))
+            b = (int(pr.get("tp_b")), int(pr.get("view_setup_b")))
+            shift = np.array([float(v) for v in pr.findtext("shift").split()]).reshape(3, 4)
+            bb = [float(v) for v in (pr.findtext("overlap_boundingbox") or "").split()]
+            out.append(dict(pair=(a, b), shift=shift, r=float(pr.findtext("correlation")),
+                            hash=float(pr.findtext("hash")), bbox=bb))
+        return out
+
+    def set_stitching_results(self, results):
+        """results: iterable of dict(pair=((tpA,setupA),(tpB,setupB)), shift 3x4, r, hash, bbox_min, bbox_max).
+        Existing results for the same pair (either direction) are replaced
+        (J/SparkPairwiseStitching.java:328-342)."""
+        sr = self.root.find("StitchingResults")
+        if sr is None:
+            sr = ET.SubElement(self.root, "StitchingResults")
+        for res in results:
+            (tpa, sa), (tpb, sb) = res["pair"]
+            for pr in list(sr.findall("PairwiseResult")):
+                ka = (int(pr.get("tp_a")), int(pr.get("view_setup_a")))
+                kb = (int(pr.get("tp_b")), int(pr.get("view_setup_b")))
+                if {ka, kb} == {(tpa, sa), (tpb, sb)}:
+                    sr.remove(pr)
+            pr = ET.SubElement(sr, "PairwiseResult", view_setup_a=str(sa), view_setup_b=str(sb), tp_a=str(tpa), tp_b=str(tpb))
+            sh = ET.SubElement(pr, "shift", type="affine")
+            sh.text = _fmt(np.asarray(res["shift"]).ravel())
+            ET.SubElement(pr, "correlation").text = repr(float(res["r"]))
+            ET.SubElement(pr, "hash").text = repr(float(res["hash"]))
+            ET.SubElement(pr, "overlap_boundingbox").text = _fmt(list(res["bbox_min"]) + list(res["bbox_max"]))
+
+
+# ---------------------------------------------------------------------------------------------
+def write_dataset_xml(path, n5_rel_path, tiles, timepoint=0):
+    """Write a fresh SpimData2 project: ``tiles`` = list of dict(setup, size_xyz, tile, translation_xyz
+    [, channel, illumination, angle]).  Used by the synthetic end-to-end configs."""
+    root = ET.Element("SpimData", version="0.2")
+    ET.SubElement(root, "BasePath", type="relative").text = "."
+    seq = ET.SubElement(root, "SequenceDescription")
+    il = ET.SubElement(seq, "ImageLoader", format="bdv.n5", version="1.0")
+    ET.SubElement(il, "n5", type="relative").text = n5_rel_path
+    vss = ET.SubElement(seq, "ViewSetups")
+    for t in tiles:
+        vs = ET.SubElement(vss, "ViewSetup")
+        ET.SubElement(vs, "id").text = str(t["setup"])
+        ET.SubElement(vs, "name").text = str(t["setup"])
+        ET.SubElement(vs, "size").text = " ".join(str(int(v)) for v in t["size_xyz"])
+        vx = ET.SubElement(vs, "voxelSize")
+        ET.SubElement(vx, "unit").text = "px"
+        ET.SubElement(vx, "size").text = "1.0 1.0 1.0"
+        at = ET.SubElement(vs, "attributes")
+        ET.SubElement(at, "illumination").text = str(t.get("illumination", 0))
+        ET.SubElement(at, "channel").text = str(t.get("channel", 0))
+        ET.SubElement(at, "tile").text = str(t.get("tile", t["setup"]))
+        ET.SubElement(at, "angle").text = str(t.get("angle", 0))
+    tp = ET.SubElement(seq, "Timepoints", type="pattern")
+    ET.SubElement(tp, "integerpattern").text = str(timepoint)
+    ET.SubElement(seq, "MissingViews")
+    vrs = ET.SubElement(root, "ViewRegistrations")
+    for t in tiles:
+        vr = ET.SubElement(vrs, "ViewRegistration", timepoint=str(timepoint), setup=str(t["setup"]))
+        vt = ET.SubElement(vr, "ViewTransform", type="affine")
+        ET.SubElement(vt, "Name").text = "Translation to Regular Grid"
+        tx, ty, tz = t["translation_xyz"]
+        ET.SubElement(vt, "affine").text = _fmt([1, 0, 0, tx, 0, 1, 0, ty, 0, 0, 1, tz])
+        vt = ET.SubElement(vr, "ViewTransform", type="affine")
+        ET.SubElement(vt, "Name").text = "calibration"
+        ET.SubElement(vt, "affine").text = _fmt([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0])
+    for tag in ("ViewInterestPoints", "BoundingBoxes", "PointSpreadFunctions", "StitchingResults", "IntensityAdjustments"):
+        ET.SubElement(root, tag)
+    tree = ET.ElementTree(root)
+    ET.indent(tree, space="  ")
+    tree.write(path, encoding="UTF-8", xml_declaration=True)
+    return path

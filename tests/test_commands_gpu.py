@@ -1,0 +1,46 @@
+"""End-to-end next-row test (BASELINE config 1 shape, reduced size): SpimData2 XML + BDV-N5 in,
+`stitching` results into the XML, `create-fusion-container` + `affine-fusion` into an N5 container."""
+import numpy as np
+import pytest
+
+from oracle import fusion_oracle as fo
+from tests import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def test_stitching_then_fusion_end_to_end(ctx, tmp_path):
+    import bsgpu
+    from bsgpu import commands, n5 as bn5, spimdata
+    n, ov = 96, 40
+    nominal = n - ov
+    G = synth.field((n + 16, n + 16, 2 * n + 16), seed=3, sigma=1.0)
+    A = synth.tile_from(G, (8, 8, 8), (n, n, n), 1)
+    B = synth.tile_from(G, (8 + 1, 8 - 2, 8 + nominal + 3), (n, n, n), 2)   # true offset = nominal + (3,-2,1)
+    store = bn5.N5Store(str(tmp_path / "dataset.n5"), create=True)
+    bn5.write_bdv_setup(store, 0, 0, A, (64, 64, 64))
+    bn5.write_bdv_setup(store, 1, 0, B, (64, 64, 64), compression="gzip")
+    xml = spimdata.write_dataset_xml(str(tmp_path / "dataset.xml"), "dataset.n5", [
+        dict(setup=0, size_xyz=(n, n, n), tile=0, translation_xyz=(0, 0, 0)),
+        dict(setup=1, size_xyz=(n, n, n), tile=1, translation_xyz=(nominal, 0, 0))])
+
+    raw = commands.stitching(xml, ctx, downsampling=(1, 1, 1))
+    assert len(raw) == 1 and raw[0] is not None
+    res = spimdata.SpimData2.load(xml).stitching_results()
+    assert len(res) == 1 and res[0]["pair"] == ((0, 0), (0, 1)) and res[0]["r"] > 0.9
+    assert np.all(np.rint(res[0]["shift"][:, 3]) == (3, -2, 1))          # planted registration error recovered
+
+    out = str(tmp_path / "fused.n5")
+    commands.create_fusion_container(xml, out, block_size=(32, 32, 32))
+    ds = commands.affine_fusion(out, ctx, "AVG_BLEND", block_scale=(2, 2, 1))
+    st, meta = bn5.read_fusion_container(out)
+    fused = st.read_volume(ds)
+    assert meta["bb_min"] == [0, 0, 0] and meta["bb_max"] == [nominal + n - 1, n - 1, n - 1]
+    views = []
+    for vol, t in ((A, (0, 0, 0)), (B, (nominal, 0, 0))):
+        M = synth.translation(t)
+        border, rng = fo.adjust_blending(M)
+        views.append(fo.View(vol, M, border, rng))
+    want = fo.fuse_block(views, (0, 0, 0), (nominal + n, n, n), fo.AVG_BLEND)
+    err = np.abs(fused - want) / np.maximum(np.abs(want), 1.0)
+    assert (err > 1e-4).mean() < 1e-3 and fused.shape == want.shape

@@ -1,0 +1,106 @@
+"""Next rows: N5 block codec + container contract, SpimData2 XML -- CPU only."""
+import gzip
+import os
+import struct
+
+import numpy as np
+import pytest
+
+import bsgpu
+from bsgpu import n5 as bn5, spimdata
+from tests import synth
+
+
+def test_n5_block_header_and_byte_order_known_answer(tmp_path):
+    st = bn5.N5Store(str(tmp_path / "a.n5"), create=True)
+    st.create_dataset("d", (5, 4, 3), (4, 4, 4), np.uint16)
+    blk = np.arange(2 * 3 * 4, dtype=np.uint16).reshape(2, 3, 4) + 256   # [z,y,x]
+    st.write_block("d", (0, 0, 0), blk)
+    raw = open(tmp_path / "a.n5" / "d" / "0" / "0" / "0", "rb").read()
+    # mode 0, ndim 3, dims x=4,y=3,z=2 big-endian, then big-endian elements x-fastest
+    assert raw[:16] == struct.pack(">HHIII", 0, 3, 4, 3, 2)
+    assert raw[16:20] == bytes([1, 0, 1, 1])                       # 256, 257
+    assert np.array_equal(st.read_block("d", (0, 0, 0)), blk)
+    assert st.read_block("d", (1, 0, 0)) is None
+    a = st.dataset_attributes("d")
+    assert a["dimensions"] == [5, 4, 3] and a["blockSize"] == [4, 4, 4] and a["dataType"] == "uint16"
+    assert a["compression"] == {"type": "raw"}
+
+
+@pytest.mark.parametrize("comp", ["raw", "gzip"])
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32, np.uint8])
+def test_n5_volume_roundtrip_ragged_edges(tmp_path, comp, dtype):
+    vol = (np.random.default_rng(0).random((19, 33, 50)) * 200).astype(dtype)
+    st = bn5.N5Store(str(tmp_path / "v.n5"), create=True)
+    st.write_volume("setup0/timepoint0/s0", vol, (16, 16, 16), comp)
+    assert np.array_equal(st.read_volume("setup0/timepoint0/s0"), vol)
+    if comp == "gzip":   # payload is a standard gzip member
+        raw = open(tmp_path / "v.n5" / "setup0" / "timepoint0" / "s0" / "0" / "0" / "0", "rb").read()
+        assert len(gzip.decompress(raw[16:])) == 16 ** 3 * np.dtype(dtype).itemsize
+
+
+def test_save_block_splits_superblock_like_n5utils(tmp_path):
+    st = bn5.N5Store(str(tmp_path / "o.n5"), create=True)
+    st.create_dataset("ch0tp0/s0", (40, 40, 20), (16, 16, 16), np.float32)
+    sb = np.random.default_rng(1).random((16, 24, 32)).astype(np.float32)   # super-block at grid (1,1,0): clipped
+    st.save_block("ch0tp0/s0", sb[:, :24, :24], (1, 1, 0))
+    out = st.read_volume("ch0tp0/s0")
+    assert np.array_equal(out[0:16, 16:40, 16:40], sb[:, :24, :24])
+    assert not out[:, :16, :].any()
+
+
+def test_fusion_container_contract_roundtrip(tmp_path):
+    bn5.create_fusion_container(str(tmp_path / "f.n5"), "/data/dataset.xml", (-3, 0, 5), (124, 99, 68), (64, 64, 32),
+                                "uint16", 100.0, 4000.0, anisotropy_factor=2.5)
+    store, m = bn5.read_fusion_container(str(tmp_path / "f.n5"))
+    assert m["format"] == "N5" and m["input_xml"] == "/data/dataset.xml"
+    assert m["bb_min"] == [-3, 0, 5] and m["bb_max"] == [124, 99, 68] and m["block_size"] == [64, 64, 32]
+    assert m["dtype"] == "uint16" and m["min_intensity"] == 100.0 and m["max_intensity"] == 4000.0
+    assert m["preserve_anisotropy"] is True and m["anisotropy_factor"] == 2.5
+    ds = m["mr_infos"][0][0]
+    assert ds["dataset"] == "ch0tp0/s0" and ds["dimensions"] == [128, 100, 64]
+    assert store.dataset_attributes("ch0tp0/s0")["dataType"] == "uint16"
+    with pytest.raises(KeyError):
+        bn5.read_fusion_container(str(bn5.N5Store(str(tmp_path / "plain.n5"), create=True).root))
+
+
+def _project(tmp_path, n=3):
+    tiles = [dict(setup=i, size_xyz=(64, 48, 32), tile=i, translation_xyz=(50.0 * i, 1.5 * i, 0.0)) for i in range(n)]
+    return spimdata.write_dataset_xml(str(tmp_path / "dataset.xml"), "dataset.n5", tiles)
+
+
+def test_spimdata_parse_registrations_and_pairs(tmp_path):
+    xml = _project(tmp_path)
+    d = spimdata.SpimData2.load(xml)
+    assert d.setups[1].size == (64, 48, 32) and d.setups[2].attributes["tile"] == 2
+    assert d.image_loader() == ("bdv.n5", str(tmp_path / "dataset.n5"))
+    assert np.allclose(d.model(0, 2), synth.translation((100.0, 3.0, 0.0)))
+    # 64-wide tiles every 50 px: neighbours overlap, tiles 0 and 2 do not (100 > 63)
+    assert d.stitching_pairs() == [((0, 0), (0, 1)), ((0, 1), (0, 2))]
+
+
+def test_spimdata_transform_list_order_index0_applied_last(tmp_path):
+    xml = _project(tmp_path, n=1)
+    d = spimdata.SpimData2.load(xml)
+    S = np.array([[2.0, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]])
+    d.registrations[(0, 0)] = [("grid", synth.translation((10, 0, 0))), ("scale", S)]
+    # pixel (1,0,0) -> scale first (2,0,0) -> then translate (12,0,0)
+    M = d.model(0, 0)
+    assert np.allclose(M @ np.array([1, 0, 0, 1.0]), [12, 0, 0])
+
+
+def test_stitching_results_written_replaced_and_reloaded(tmp_path):
+    xml = _project(tmp_path)
+    d = spimdata.SpimData2.load(xml)
+    res = dict(pair=((0, 0), (0, 1)), shift=synth.translation((3, -2, 1)), r=0.97, hash=12.5,
+               bbox_min=(50, 1.5, 0), bbox_max=(63, 47, 31))
+    d.set_stitching_results([res])
+    d.set_stitching_results([dict(res, pair=((0, 1), (0, 0)), r=0.5)])      # b->a replaces a->b
+    d.save()
+    assert os.path.exists(xml + "~1")
+    back = spimdata.SpimData2.load(xml).stitching_results()
+    assert len(back) == 1 and back[0]["pair"] == ((0, 1), (0, 0)) and back[0]["r"] == 0.5
+    assert np.allclose(back[0]["shift"], synth.translation((3, -2, 1))) and back[0]["bbox"] == [50, 1.5, 0, 63, 47, 31]
+    h1 = spimdata.SpimData2.transform_hash(d.registrations[(0, 0)], d.registrations[(0, 1)])
+    h2 = spimdata.SpimData2.transform_hash(d.registrations[(0, 0)], d.registrations[(0, 2)])
+    assert h1 != h2
