@@ -111,6 +111,7 @@ void bs_destroy(bs_ctx* ctx) {
     for (int i = 0; i < bs_ctx::kFuseSlots; ++i)
         if (ctx->fuse_slot_ev[i]) cudaEventDestroy(ctx->fuse_slot_ev[i]);
     if (ctx->fuse_out) cudaFree(ctx->fuse_out);
+    if (ctx->fuse_plan) cudaFree(ctx->fuse_plan);
     cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;

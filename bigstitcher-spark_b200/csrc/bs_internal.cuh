@@ -66,6 +66,8 @@ struct bs_ctx {
     int fuse_next_slot = 0;
     cudaEvent_t fuse_slot_ev[kFuseSlots] = {};
     bool fuse_slot_used[kFuseSlots] = {};
+    void* fuse_plan = nullptr;        // per-tile view lists of the current fusion call
+    size_t fuse_plan_cap = 0;
     void* fuse_out = nullptr;         // device staging for host outputs
     size_t fuse_out_cap = 0;
     int sm_count = 148;

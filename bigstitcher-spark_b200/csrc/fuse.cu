@@ -16,7 +16,7 @@
 #define FUSE_TX 32
 #define FUSE_TY 8
 #define FUSE_ZT 8
-#define FUSE_CHUNK 64
+#define FUSE_CHUNK 32
 #define FUSE_MAX_LUT 256
 
 struct FuseViewDev {
@@ -41,6 +41,7 @@ struct FuseArgs {
     float* acc_wi;         // accumulate mode
     float* acc_w;
     int no_stage;          // debug: force the global-gather path (env BS_FUSE_NO_STAGE)
+    const struct TilePlan* plan;   // per-tile view lists from fuse_plan_kernel (or nullptr)
 };
 
 template <typename T>
@@ -211,6 +212,85 @@ __device__ __forceinline__ bool blend_axis(float l, float dm1, float border, flo
     return true;
 }
 
+// Cull one view against one output tile and derive its tile constants (double precision once per
+// (tile, view); the per-voxel loop is float and tile-relative).  Returns false when the view's
+// source AABB of the tile misses [0, dim-1] (+-1e-3).
+__device__ __forceinline__ bool make_view_tile(const FuseViewDev& v, double cx0, double cy0, double cz0, double ex,
+                                               double ey, double ez, bool allow_stage, ViewTile& t) {
+    bool hit = true, fits = allow_stage, interior = true, plateau = true;
+    const double c0[3] = {cx0, cy0, cz0};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double m0 = v.inv[4 * r], m1 = v.inv[4 * r + 1], m2 = v.inv[4 * r + 2];
+        const double org = fma(m0, c0[0], fma(m1, c0[1], fma(m2, c0[2], v.inv[4 * r + 3])));
+        const double lo = org + fmin(0.0, m0 * ex) + fmin(0.0, m1 * ey) + fmin(0.0, m2 * ez);
+        const double hi = org + fmax(0.0, m0 * ex) + fmax(0.0, m1 * ey) + fmax(0.0, m2 * ez);
+        const int dim = v.dims[r];
+        if (hi < -1e-3 || lo > (double)(dim - 1) + 1e-3) hit = false;
+        // taps floor(s) .. floor(s)+1 of every in-range s; eps covers float rounding of s
+        const double eps = 2e-3 + 2e-7 * fmax(fabs(lo), fabs(hi));
+        const int f0 = max((int)floor(fmax(lo - eps, 0.0)), 0);
+        const int f1 = min((int)floor(fmin(hi + eps, (double)(dim - 1))) + 1, dim - 1);
+        const int cap = r == 0 ? FS_X : (r == 1 ? FS_Y : FS_Z);
+        int g0 = f0;
+        if (r == 0) g0 &= ~3;                      // 4-voxel aligned box origin along x (vector staging)
+        if (f1 - g0 + 1 > cap - 1) fits = false;   // one spare row/column: a tap at weight 0 may touch f1 + 1
+        if (f1 + 1 > dim - 1) interior = false;
+        if (!(lo - eps - (double)v.border[r] >= (double)v.range[r] &&
+              (double)(dim - 1) - (hi + eps) - (double)v.border[r] >= (double)v.range[r])) plateau = false;
+        t.b0[r] = g0;
+        t.o[r] = (float)(org - (double)g0);
+        t.m[3 * r] = (float)m0; t.m[3 * r + 1] = (float)m1; t.m[3 * r + 2] = (float)m2;
+        t.dims[r] = dim;
+        t.border[r] = v.border[r];
+        t.range[r] = v.range[r];
+        t.inv_range[r] = 1.0f / v.range[r];
+    }
+    t.data = v.data;
+    t.content = v.content;
+    t.dtype = v.dtype;
+    t.staged = fits ? 1 : 0;
+    t.interior = interior ? 1 : 0;
+    t.plateau = plateau ? 1 : 0;
+    t.vec4 = (v.dtype == BS_DTYPE_U16 && (v.dims[0] & 3) == 0 && ((size_t)v.data & 7) == 0 &&
+              t.b0[0] + FS_X <= v.dims[0]) ? 1 : 0;
+    return hit;
+}
+
+// Plan pre-pass: one thread per output tile walks the (ViewId-sorted) view list and writes the
+// tile's active views with their constants.  It takes the culling / double-precision set-up out of
+// the fusion kernel's critical path (there it was a serial prologue of five barriers per CTA).
+#define FUSE_PLAN_MAXV 8
+struct TilePlan {
+    int count;
+    int overflow;        // more than FUSE_PLAN_MAXV active views: the fusion kernel culls this tile itself
+    ViewTile v[FUSE_PLAN_MAXV];
+};
+
+__global__ void fuse_plan_kernel(const FuseViewDev* __restrict__ views, int nviews, FuseArgs a, TilePlan* plan,
+                                 int gx, int gy, int gz, int linear) {
+    const int tile = blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= gx * gy * gz) return;
+    const int bx = tile % gx, by = (tile / gx) % gy, bz = tile / (gx * gy);
+    const int z0 = bz * FUSE_ZT;
+    const double cx0 = (double)(a.bmin[0] + (long long)bx * FUSE_TX);
+    const double cy0 = (double)(a.bmin[1] + (long long)by * FUSE_TY);
+    const double cz0 = (double)(a.bmin[2] + z0);
+    const double ex = (double)(min(FUSE_TX, a.size[0] - bx * FUSE_TX) - 1);
+    const double ey = (double)(min(FUSE_TY, a.size[1] - by * FUSE_TY) - 1);
+    const double ez = (double)(min(FUSE_ZT, a.size[2] - z0) - 1);
+    TilePlan& p = plan[tile];
+    int count = 0, overflow = 0;
+    for (int vi = 0; vi < nviews; ++vi) {
+        ViewTile t;
+        if (!make_view_tile(views[vi], cx0, cy0, cz0, ex, ey, ez, linear && a.no_stage == 0, t)) continue;
+        if (count < FUSE_PLAN_MAXV) p.v[count++] = t;
+        else overflow = 1;
+    }
+    p.count = count;
+    p.overflow = overflow;
+}
+
 // KIND 0: weighted average family (AVG, AVG_BLEND, *_CONTENT); KIND 1: winner family.
 // ACCUM: add partial sums into acc_wi/acc_w instead of producing the final voxel.
 //
@@ -221,7 +301,7 @@ __device__ __forceinline__ bool blend_axis(float l, float dm1, float border, flo
 // memory.  Footprints that do not fit the box (down-scaling, strong rotation) and nearest-
 // neighbour sampling gather from global memory through L1/L2 instead.
 template <int KIND, bool LINEAR, int OUT, bool ACCUM>
-__global__ void __launch_bounds__(FUSE_TX* FUSE_TY, 3)
+__global__ void __launch_bounds__(FUSE_TX* FUSE_TY, 4)
 fuse_kernel(const FuseViewDev* __restrict__ views, int nviews, FuseArgs a) {
     __shared__ int s_active[FUSE_CHUNK];
     __shared__ ViewTile s_vt[FUSE_CHUNK];
@@ -243,90 +323,61 @@ fuse_kernel(const FuseViewDev* __restrict__ views, int nviews, FuseArgs a) {
     if (a.lut_n > 0)
         for (int i = tid; i < a.lut_n + 2; i += NT) s_lut[i] = a.lut[i];
 
-    float acc0[FUSE_ZT];  // KIND0: sum w*I ; KIND1: best value
-    float acc1[FUSE_ZT];  // KIND0: sum w   ; KIND1: best weight (CLOSEST) / have flag
+    // accumulators live in shared memory ([k][thread], private to the owning thread) so that the z loop
+    // can stay ROLLED: the fully unrolled version was 9.4k SASS instructions and stalled on
+    // instruction fetch (ncu: no_instruction was the top stall reason)
+    __shared__ float s_acc0[FUSE_ZT][FUSE_TX * FUSE_TY];  // KIND0: sum w*I ; KIND1: best value
+    __shared__ float s_acc1[FUSE_ZT][FUSE_TX * FUSE_TY];  // KIND0: sum w   ; KIND1: best weight / have flag
 #pragma unroll
-    for (int k = 0; k < FUSE_ZT; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
+    for (int k = 0; k < FUSE_ZT; ++k) { s_acc0[k][tid] = 0.f; s_acc1[k][tid] = 0.f; }
 
     const float tx = (float)threadIdx.x, ty = (float)threadIdx.y;
     const int nz = min(FUSE_ZT, a.size[2] - z0);
 
-    for (int chunk = 0; chunk < nviews; chunk += FUSE_CHUNK) {
-        __syncthreads();
-        if (tid == 0) s_nactive = 0;
-        __syncthreads();
-        // ---- cull: source AABB of the tile's corners against [0, dim-1] (+-1e-3 guard)
-        const double cx0 = (double)(a.bmin[0] + (long long)blockIdx.x * FUSE_TX);
-        const double cy0 = (double)(a.bmin[1] + (long long)blockIdx.y * FUSE_TY);
-        const double cz0 = (double)(a.bmin[2] + z0);
-        const double ex = (double)(min(FUSE_TX, a.size[0] - (int)blockIdx.x * FUSE_TX) - 1);
-        const double ey = (double)(min(FUSE_TY, a.size[1] - (int)blockIdx.y * FUSE_TY) - 1);
-        const double ez = (double)(nz - 1);
-        for (int vi = chunk + tid; vi < min(nviews, chunk + FUSE_CHUNK); vi += NT) {
-            const FuseViewDev& v = views[vi];
-            bool hit = true;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const double m0 = v.inv[4 * r], m1 = v.inv[4 * r + 1], m2 = v.inv[4 * r + 2];
-                const double org = fma(m0, cx0, fma(m1, cy0, fma(m2, cz0, v.inv[4 * r + 3])));
-                const double lo = org + fmin(0.0, m0 * ex) + fmin(0.0, m1 * ey) + fmin(0.0, m2 * ez);
-                const double hi = org + fmax(0.0, m0 * ex) + fmax(0.0, m1 * ey) + fmax(0.0, m2 * ez);
-                if (hi < -1e-3 || lo > (double)(v.dims[r] - 1) + 1e-3) hit = false;
+    const TilePlan* tp = a.plan ? a.plan + ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x : nullptr;
+    const bool planned = tp != nullptr && tp->overflow == 0;   // CTA-uniform
+    for (int chunk = 0; chunk < (planned ? 1 : nviews); chunk += FUSE_CHUNK) {
+        int nact;
+        if (planned) {
+            // tile constants were prepared by fuse_plan_kernel: copy them to shared memory
+            __syncthreads();
+            nact = tp->count;
+            const int nwords = nact * (int)(sizeof(ViewTile) / 4);
+            const int* src = reinterpret_cast<const int*>(tp->v);
+            int* dst = reinterpret_cast<int*>(s_vt);
+            for (int i = tid; i < nwords; i += NT) dst[i] = __ldg(src + i);
+            __syncthreads();
+        } else {
+            __syncthreads();
+            if (tid == 0) s_nactive = 0;
+            __syncthreads();
+            const double cx0 = (double)(a.bmin[0] + (long long)blockIdx.x * FUSE_TX);
+            const double cy0 = (double)(a.bmin[1] + (long long)blockIdx.y * FUSE_TY);
+            const double cz0 = (double)(a.bmin[2] + z0);
+            const double ex = (double)(min(FUSE_TX, a.size[0] - (int)blockIdx.x * FUSE_TX) - 1);
+            const double ey = (double)(min(FUSE_TY, a.size[1] - (int)blockIdx.y * FUSE_TY) - 1);
+            const double ez = (double)(nz - 1);
+            // cull: threads over the views of this chunk
+            for (int vi = chunk + tid; vi < min(nviews, chunk + FUSE_CHUNK); vi += NT) {
+                ViewTile t;
+                if (make_view_tile(views[vi], cx0, cy0, cz0, ex, ey, ez, LINEAR && a.no_stage == 0, t))
+                    s_active[atomicAdd(&s_nactive, 1)] = vi;
             }
-            if (hit) s_active[atomicAdd(&s_nactive, 1)] = vi;
-        }
-        __syncthreads();
-        const int nact = s_nactive;
-        // deterministic view order (ascending ViewId): sort the short active list
-        if (tid == 0) {
-            for (int i = 1; i < nact; ++i) {
-                int key = s_active[i], j = i - 1;
-                while (j >= 0 && s_active[j] > key) { s_active[j + 1] = s_active[j]; --j; }
-                s_active[j + 1] = key;
+            __syncthreads();
+            nact = s_nactive;
+            // deterministic view order (ascending ViewId): sort the short active list
+            if (tid == 0) {
+                for (int i = 1; i < nact; ++i) {
+                    int key = s_active[i], j = i - 1;
+                    while (j >= 0 && s_active[j] > key) { s_active[j + 1] = s_active[j]; --j; }
+                    s_active[j + 1] = key;
+                }
             }
+            __syncthreads();
+            for (int ai = tid; ai < nact; ai += NT)
+                make_view_tile(views[s_active[ai]], cx0, cy0, cz0, ex, ey, ez, LINEAR && a.no_stage == 0, s_vt[ai]);
+            __syncthreads();
         }
-        __syncthreads();
-        // ---- per-view tile constants
-        for (int ai = tid; ai < nact; ai += NT) {
-            const FuseViewDev& v = views[s_active[ai]];
-            ViewTile& t = s_vt[ai];
-            bool fits = LINEAR && a.no_stage == 0;
-            bool interior = true, plateau = true;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const double m0 = v.inv[4 * r], m1 = v.inv[4 * r + 1], m2 = v.inv[4 * r + 2];
-                const double org = fma(m0, cx0, fma(m1, cy0, fma(m2, cz0, v.inv[4 * r + 3])));
-                const double lo = org + fmin(0.0, m0 * ex) + fmin(0.0, m1 * ey) + fmin(0.0, m2 * ez);
-                const double hi = org + fmax(0.0, m0 * ex) + fmax(0.0, m1 * ey) + fmax(0.0, m2 * ez);
-                // taps floor(s) .. floor(s)+1 of every in-range s; eps covers float rounding of s
-                const double eps = 2e-3 + 2e-7 * fmax(fabs(lo), fabs(hi));
-                const int f0 = max((int)floor(fmax(lo - eps, 0.0)), 0);
-                const int f1 = min((int)floor(fmin(hi + eps, (double)(v.dims[r] - 1))) + 1, v.dims[r] - 1);
-                const int cap = r == 0 ? FS_X : (r == 1 ? FS_Y : FS_Z);
-                int g0 = f0;
-                if (r == 0) g0 &= ~3;                      // 4-voxel aligned box origin along x (vector staging)
-                if (f1 - g0 + 1 > cap - 1) fits = false;   // one spare row/column: a tap at weight 0 may touch f1 + 1
-                if (f1 + 1 > v.dims[r] - 1) interior = false;
-                if (!(lo - eps - (double)v.border[r] >= (double)v.range[r] &&
-                      (double)(v.dims[r] - 1) - (hi + eps) - (double)v.border[r] >= (double)v.range[r])) plateau = false;
-                t.b0[r] = g0;
-                t.o[r] = (float)(org - (double)g0);
-                t.m[3 * r] = (float)m0; t.m[3 * r + 1] = (float)m1; t.m[3 * r + 2] = (float)m2;
-                t.dims[r] = v.dims[r];
-                t.border[r] = v.border[r];
-                t.range[r] = v.range[r];
-                t.inv_range[r] = 1.0f / v.range[r];
-            }
-            t.data = v.data;
-            t.content = v.content;
-            t.dtype = v.dtype;
-            t.staged = fits ? 1 : 0;
-            t.interior = interior ? 1 : 0;
-            t.plateau = plateau ? 1 : 0;
-            t.vec4 = (v.dtype == BS_DTYPE_U16 && (v.dims[0] & 3) == 0 && ((size_t)v.data & 7) == 0 &&
-                      t.b0[0] + FS_X <= v.dims[0]) ? 1 : 0;
-        }
-        __syncthreads();
 
         for (int ai = 0; ai < nact; ++ai) {
             const ViewTile& t = s_vt[ai];
@@ -346,10 +397,9 @@ fuse_kernel(const FuseViewDev* __restrict__ views, int nviews, FuseArgs a) {
             const float bx = (float)t.b0[0], by = (float)t.b0[1], bz = (float)t.b0[2];
             const float dm1x = (float)(t.dims[0] - 1), dm1y = (float)(t.dims[1] - 1), dm1z = (float)(t.dims[2] - 1);
             const bool do_blend = use_blend && !t.plateau;
-            const bool interior = t.interior != 0;
-#pragma unroll
-            for (int k = 0; k < FUSE_ZT; ++k, rx += sxk, ry += syk, rz += szk) {
-                if (k >= nz) break;
+            const int mode = staged ? (t.interior ? 0 : 1) : 2;
+#pragma unroll 1
+            for (int k = 0; k < nz; ++k, rx += sxk, ry += syk, rz += szk) {
                 const float fx = rx + bx, fy = ry + by, fz = rz + bz;  // absolute source coordinate
                 if (!(fx >= 0.f && fx <= dm1x && fy >= 0.f && fy <= dm1y && fz >= 0.f && fz <= dm1z)) continue;
                 float w = 1.f;
@@ -359,45 +409,46 @@ fuse_kernel(const FuseViewDev* __restrict__ views, int nviews, FuseArgs a) {
                     if (!blend_axis(fz, dm1z, t.border[2], t.inv_range[2], a.lut_n, s_lut, w)) continue;
                 }
                 float val;
-                if (staged) val = interior ? sample_staged<true>(s_stage, t, fmaxf(rx, 0.f), fmaxf(ry, 0.f), fmaxf(rz, 0.f))
-                                           : sample_staged<false>(s_stage, t, fmaxf(rx, 0.f), fmaxf(ry, 0.f), fmaxf(rz, 0.f));
+                if (mode == 0) val = sample_staged<true>(s_stage, t, fmaxf(rx, 0.f), fmaxf(ry, 0.f), fmaxf(rz, 0.f));
+                else if (mode == 1) val = sample_staged<false>(s_stage, t, fmaxf(rx, 0.f), fmaxf(ry, 0.f), fmaxf(rz, 0.f));
                 else val = sample_any<LINEAR>(t.data, t.dtype, t.dims[0], t.dims[1], t.dims[2], fx, fy, fz);
                 if (KIND == 0) {
                     if (use_content) {
                         if (staged) w *= sample_staged<false>(s_stage_c, t, fmaxf(rx, 0.f), fmaxf(ry, 0.f), fmaxf(rz, 0.f));
                         else w *= sample<float, LINEAR>(t.content, t.dims[0], t.dims[1], t.dims[2], fx, fy, fz);
                     }
-                    acc0[k] += w * val;
-                    acc1[k] += w;
+                    s_acc0[k][tid] += w * val;
+                    s_acc1[k][tid] += w;
                 } else {
                     if (!(w > 0.f)) continue;
+                    const float c0 = s_acc0[k][tid], c1 = s_acc1[k][tid];
                     if (ft == BS_FUSE_MAX_INTENSITY) {
-                        if (acc1[k] == 0.f || val > acc0[k]) acc0[k] = val;
-                        acc1[k] = 1.f;
+                        if (c1 == 0.f || val > c0) s_acc0[k][tid] = val;
+                        s_acc1[k][tid] = 1.f;
                     } else if (ft == BS_FUSE_LOWEST_VIEWID_WINS) {
-                        if (acc1[k] == 0.f) { acc0[k] = val; acc1[k] = 1.f; }
+                        if (c1 == 0.f) { s_acc0[k][tid] = val; s_acc1[k][tid] = 1.f; }
                     } else if (ft == BS_FUSE_HIGHEST_VIEWID_WINS) {
-                        acc0[k] = val; acc1[k] = 1.f;
+                        s_acc0[k][tid] = val; s_acc1[k][tid] = 1.f;
                     } else {  // CLOSEST_PIXEL_WINS: largest blending weight wins
-                        if (w > acc1[k]) { acc0[k] = val; acc1[k] = w; }
+                        if (w > c1) { s_acc0[k][tid] = val; s_acc1[k][tid] = w; }
                     }
                 }
             }
         }
     }
     if (!valid) return;
-#pragma unroll
-    for (int k = 0; k < FUSE_ZT; ++k) {
-        if (k >= nz) break;
+#pragma unroll 1
+    for (int k = 0; k < nz; ++k) {
         const size_t o = ((size_t)(z0 + k) * a.size[1] + y) * a.size[0] + x;
+        const float c0 = s_acc0[k][tid], c1 = s_acc1[k][tid];
         if (ACCUM) {
-            a.acc_wi[o] += acc0[k];
-            a.acc_w[o] += acc1[k];
+            a.acc_wi[o] += c0;
+            a.acc_w[o] += c1;
             continue;
         }
         float res;
-        if (KIND == 0) res = acc1[k] > 0.f ? acc0[k] / acc1[k] : 0.f;
-        else res = acc1[k] > 0.f ? acc0[k] : 0.f;
+        if (KIND == 0) res = c1 > 0.f ? c0 / c1 : 0.f;
+        else res = c1 > 0.f ? c0 : 0.f;
         if (OUT == BS_DTYPE_F32) {
             __stcs((float*)a.out + o, res);
         } else {
@@ -577,17 +628,30 @@ static int fuse_launch(bs_ctx* ctx, const FusePrepared& prep, const bs_fuse_para
     const FuseViewDev* v = prep.views_dev;
     const bool winner = p->fusion_type >= BS_FUSE_MAX_INTENSITY;
     const bool lin = p->interpolation == 1;
+    FuseArgs a2 = a;
+    {
+        const char* e = getenv("BS_FUSE_NO_PLAN");
+        const long long ntiles = (long long)grid.x * grid.y * grid.z;
+        if (!(e && *e && *e != '0') && prep.nviews > 0 && ntiles * (long long)sizeof(TilePlan) <= (256LL << 20)) {
+            int rc = bs_ensure_dev(ctx, &ctx->fuse_plan, &ctx->fuse_plan_cap, (size_t)ntiles * sizeof(TilePlan));
+            if (rc) return rc;
+            a2.plan = (const TilePlan*)ctx->fuse_plan;
+            bs_launch_scope scope(ctx, "fuse_plan");
+            fuse_plan_kernel<<<(unsigned)((ntiles + 127) / 128), 128, 0, ctx->stream>>>(
+                v, prep.nviews, a, (TilePlan*)ctx->fuse_plan, (int)grid.x, (int)grid.y, (int)grid.z, lin ? 1 : 0);
+        }
+    }
     {
         bs_launch_scope scope(ctx, "fuse");
         if (accum) {
-            if (lin) launch_out<0, true, true>(p->out_dtype, grid, block, ctx->stream, v, prep.nviews, a);
-            else launch_out<0, false, true>(p->out_dtype, grid, block, ctx->stream, v, prep.nviews, a);
+            if (lin) launch_out<0, true, true>(p->out_dtype, grid, block, ctx->stream, v, prep.nviews, a2);
+            else launch_out<0, false, true>(p->out_dtype, grid, block, ctx->stream, v, prep.nviews, a2);
         } else if (!winner) {
-            if (lin) launch_out<0, true, false>(p->out_dtype, grid, block, ctx->stream, v, prep.nviews, a);
-            else launch_out<0, false, false>(p->out_dtype, grid, block, ctx->stream, v, prep.nviews, a);
+            if (lin) launch_out<0, true, false>(p->out_dtype, grid, block, ctx->stream, v, prep.nviews, a2);
+            else launch_out<0, false, false>(p->out_dtype, grid, block, ctx->stream, v, prep.nviews, a2);
         } else {
-            if (lin) launch_out<1, true, false>(p->out_dtype, grid, block, ctx->stream, v, prep.nviews, a);
-            else launch_out<1, false, false>(p->out_dtype, grid, block, ctx->stream, v, prep.nviews, a);
+            if (lin) launch_out<1, true, false>(p->out_dtype, grid, block, ctx->stream, v, prep.nviews, a2);
+            else launch_out<1, false, false>(p->out_dtype, grid, block, ctx->stream, v, prep.nviews, a2);
         }
     }
     BS_CUDA(ctx, cudaGetLastError());
