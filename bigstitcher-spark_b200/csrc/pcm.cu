@@ -636,6 +636,71 @@ __global__ void __launch_bounds__(PCM_THREADS, 3) k_fft_strided(const __grid_con
     }
 }
 
+// Persistent, software-pipelined variant of mode 0: each CTA walks its tiles with three rotating
+// shared-memory buffers; the NEXT tile is pulled in with cp.async (LDGSTS, 16 B per thread and
+// request, no register staging) while the current one is transformed and stored.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct StridedPipeArgs {
+    StridedArgs s;
+    int tiles_x;     // pitch / TW
+    int n_other;     // blockIdx.y extent of the non-persistent kernel
+    int n_tiles;     // tiles_x * n_other * n_img
+};
+
+template <class F>
+__global__ void __launch_bounds__(PCM_THREADS, 2) k_fft_strided_pipe(const __grid_constant__ StridedPipeArgs p) {
+    const StridedArgs& a = p.s;
+    const int tshift = F::kStatic ? F::LSHIFT : a.tshift;
+    const int TW = 1 << tshift, N = F::kStatic ? F::N : a.plan.n;
+    const int twpad = (N + 1) & ~1;
+    float2* tw = bs_sm;
+    float2* B[3];
+    B[0] = bs_sm + twpad;
+    B[1] = B[0] + (size_t)N * TW;
+    B[2] = B[1] + (size_t)N * TW;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = a.tw[i];
+    const int vshift = tshift - 1, vmask = (1 << vshift) - 1, nvec = N << vshift;
+
+    auto tile_ptr = [&](int t) -> float2* {
+        const int tx = t % p.tiles_x;
+        const int r = t / p.tiles_x;
+        const int o = r % p.n_other, im = r / p.n_other;
+        return (im ? a.b : a.a) + (size_t)o * a.ostride + (size_t)tx * TW;
+    };
+    auto prefetch = [&](int t, float2* dst) {
+        const float2* g = tile_ptr(t);
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x)
+            cp_async16(d4 + i, reinterpret_cast<const float4*>(g + (long long)(i >> vshift) * a.estride) + (i & vmask));
+        cp_async_commit();
+    };
+
+    int t = blockIdx.x;
+    if (t < p.n_tiles) prefetch(t, B[0]);
+    for (int it = 0; t < p.n_tiles; t += gridDim.x, ++it) {
+        float2* cur = B[(2 * it) % 3];
+        float2* pong = B[(2 * it + 1) % 3];
+        float2* nxt = B[(2 * it + 2) % 3];
+        const int tn = t + gridDim.x;
+        if (tn < p.n_tiles) {
+            prefetch(tn, nxt);
+            cp_async_wait<1>();   // everything but the newest group (the next tile) has landed
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const float2* res = F::run(cur, pong, tw, a.plan, tshift, TW, 1);
+        tile_store(tile_ptr(t), res, a.estride, N, tshift);
+        __syncthreads();   // res / cur may be overwritten by the next iteration's prefetch and FFT
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // x pass, complex -> real, in place
 
@@ -765,34 +830,43 @@ __global__ void __launch_bounds__(PCM_THREADS) k_peaks(const __grid_constant__ P
                 const int vi = v0 + u * 32 + lane;
                 q[u] = vi < nvec ? __ldcs(rp4 + vi) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
             }
+            // phase 1 (unrolled, tiny): which of my 4 * PK_UNROLL values reach the warp threshold?
+            unsigned int mask = 0u;
 #pragma unroll
             for (int u = 0; u < PK_UNROLL; ++u) {
                 const int vi = v0 + u * 32 + lane;
                 const float c4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float v = c4[c];
-                    const int x = 4 * vi + c;
-                    bool cand = v >= top.thr && v > -INFINITY && x < a.Px;  // NaN fails both compares
-                    if (!__any_sync(0xffffffffu, cand)) continue;
+                for (int c = 0; c < 4; ++c)
+                    if (c4[c] >= top.thr && c4[c] > -INFINITY && 4 * vi + c < a.Px) mask |= 1u << (4 * u + c);
+            }
+            // phase 2 (rolled, rare): neighbour test + insertion, one candidate per lane per round
+            while (__any_sync(0xffffffffu, mask != 0u)) {
+                bool cand = mask != 0u;
+                int x = 0;
+                float v = -INFINITY;
+                if (cand) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1u;
+                    x = 4 * (v0 + (b >> 2) * 32 + lane) + (b & 3);
+                    v = rp[x];
+                    cand = v >= top.thr;   // the threshold may have risen since phase 1
+                    if (cand) cand = !(v < rp[x == 0 ? a.Px - 1 : x - 1] || v < rp[x == a.Px - 1 ? 0 : x + 1]);
                     if (cand) {
-                        cand = !(v < rp[x == 0 ? a.Px - 1 : x - 1] || v < rp[x == a.Px - 1 ? 0 : x + 1]);
-                        if (cand) {
-                            const float* rym = a.pcm + ((long long)z * a.Py + (y == 0 ? a.Py - 1 : y - 1)) * a.rowpitch;
-                            const float* ryp = a.pcm + ((long long)z * a.Py + (y == a.Py - 1 ? 0 : y + 1)) * a.rowpitch;
-                            const float* rzm = a.pcm + ((long long)(z == 0 ? a.Pz - 1 : z - 1) * a.Py + y) * a.rowpitch;
-                            const float* rzp = a.pcm + ((long long)(z == a.Pz - 1 ? 0 : z + 1) * a.Py + y) * a.rowpitch;
-                            cand = !(v < rym[x] || v < ryp[x] || v < rzm[x] || v < rzp[x]);
-                        }
+                        const float* rym = a.pcm + ((long long)z * a.Py + (y == 0 ? a.Py - 1 : y - 1)) * a.rowpitch;
+                        const float* ryp = a.pcm + ((long long)z * a.Py + (y == a.Py - 1 ? 0 : y + 1)) * a.rowpitch;
+                        const float* rzm = a.pcm + ((long long)(z == 0 ? a.Pz - 1 : z - 1) * a.Py + y) * a.rowpitch;
+                        const float* rzp = a.pcm + ((long long)(z == a.Pz - 1 ? 0 : z + 1) * a.Py + y) * a.rowpitch;
+                        cand = !(v < rym[x] || v < ryp[x] || v < rzm[x] || v < rzp[x]);
                     }
-                    unsigned m = __ballot_sync(0xffffffffu, cand);
-                    while (m) {
-                        const int src = __ffs(m) - 1;
-                        m &= m - 1;
-                        const float nv = __shfl_sync(0xffffffffu, v, src);
-                        const int nx = __shfl_sync(0xffffffffu, x, src);
-                        warp_topk_insert(top, K, nv, row * a.Px + nx, lane);
-                    }
+                }
+                unsigned m = __ballot_sync(0xffffffffu, cand);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const float nv = __shfl_sync(0xffffffffu, v, src);
+                    const int nx = __shfl_sync(0xffffffffu, x, src);
+                    warp_topk_insert(top, K, nv, row * a.Px + nx, lane);
                 }
             }
         }
@@ -1275,6 +1349,8 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c_tma<FftGeneric>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftX270L8>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_strided<FftS540>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_strided_pipe<FftS540>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_strided_pipe<FftGeneric>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftX270>, 0))) return rc;
         ctx->pcm_attr_done = true;
     }
@@ -1346,7 +1422,18 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         a.thresh = 0.f;
         dim3 grid(g.pitch >> g.tshift_y, g.P[2], 2);
         bs_launch_scope sc(ctx, "fft_y");
-        if (g.static_y) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
+        const size_t smem_pipe = ((size_t)((g.P[1] + 1) & ~1) + 3 * (size_t)g.P[1] * (1 << g.tshift_y)) * sizeof(float2);
+        if (env_int("BS_FFT_Y_PIPE", 1) && smem_pipe <= PCM_SMEM_MAX) {
+            StridedPipeArgs pp;
+            pp.s = a;
+            pp.tiles_x = g.pitch >> g.tshift_y;
+            pp.n_other = g.P[2];
+            pp.n_tiles = pp.tiles_x * pp.n_other * 2;
+            const int per_sm = std::max(1, std::min(2, (int)(PCM_SMEM_MAX / (smem_pipe + 1024))));
+            const int nctas = std::min(pp.n_tiles, ctx->sm_count * per_sm);
+            if (g.static_y) k_fft_strided_pipe<FftS540><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
+            else k_fft_strided_pipe<FftGeneric><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
+        } else if (g.static_y) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
         else k_fft_strided<FftGeneric><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
     }
     BS_CUDA(ctx, cudaGetLastError());
@@ -1378,7 +1465,18 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         a.thresh = 0.f;
         dim3 grid(g.pitch >> g.tshift_y, g.P[2], 1);
         bs_launch_scope sc(ctx, "fft_y_inv");
-        if (g.static_y) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
+        const size_t smem_pipe = ((size_t)((g.P[1] + 1) & ~1) + 3 * (size_t)g.P[1] * (1 << g.tshift_y)) * sizeof(float2);
+        if (env_int("BS_FFT_Y_PIPE", 1) && smem_pipe <= PCM_SMEM_MAX) {
+            StridedPipeArgs pp;
+            pp.s = a;
+            pp.tiles_x = g.pitch >> g.tshift_y;
+            pp.n_other = g.P[2];
+            pp.n_tiles = pp.tiles_x * pp.n_other * 1;
+            const int per_sm = std::max(1, std::min(2, (int)(PCM_SMEM_MAX / (smem_pipe + 1024))));
+            const int nctas = std::min(pp.n_tiles, ctx->sm_count * per_sm);
+            if (g.static_y) k_fft_strided_pipe<FftS540><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
+            else k_fft_strided_pipe<FftGeneric><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
+        } else if (g.static_y) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
         else k_fft_strided<FftGeneric><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
     }
     BS_CUDA(ctx, cudaGetLastError());
