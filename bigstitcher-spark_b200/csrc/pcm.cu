@@ -897,6 +897,7 @@ __global__ void __launch_bounds__(PCM_THREADS) k_peaks(const __grid_constant__ P
 typedef FftStatic<270, 4, 17, 2, PCM_THREADS, 9, 6, 5> FftX270;
 typedef FftStatic<270, 3, 9, 2, PCM_THREADS, 9, 6, 5> FftX270L8;
 typedef FftStatic<540, 3, 8, 1, PCM_THREADS, 9, 10, 6> FftS540;
+typedef FftStatic<540, 2, 4, 1, PCM_THREADS, 9, 10, 6> FftS540T4;
 
 struct GatherArgs {
     const float* pcm;
@@ -1267,7 +1268,7 @@ static int pcm_geometry(bs_ctx* ctx, const long long dims[3], const int ext[3], 
     g->static_x = allow_static && g->M == FftX270::N && (g->lshift_x == FftX270::LSHIFT || g->lshift_x == FftX270L8::LSHIFT) &&
                   (g->lshift_r2c == 3 || g->lshift_r2c == 4);
     g->static_y = allow_static && g->P[1] == FftS540::N && g->tshift_y == FftS540::LSHIFT;
-    g->static_z = allow_static && g->P[2] == FftS540::N && g->tshift_z == FftS540::LSHIFT;
+    g->static_z = allow_static && g->P[2] == FftS540::N && (g->tshift_z == FftS540::LSHIFT || g->tshift_z == FftS540T4::LSHIFT);
     return BS_OK;
 }
 
@@ -1349,6 +1350,7 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c_tma<FftGeneric>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftX270L8>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_strided<FftS540>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_strided<FftS540T4>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_strided_pipe<FftS540>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_strided_pipe<FftGeneric>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftX270>, 0))) return rc;
@@ -1449,7 +1451,8 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         a.thresh = 1e-5f;  // PhaseCorrelation2Util.normalizeInterval threshold
         dim3 grid(g.pitch >> g.tshift_z, g.P[1], 1);
         bs_launch_scope sc(ctx, "fft_z_xpower");
-        if (g.static_z) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
+        if (g.static_z && g.tshift_z == 2) k_fft_strided<FftS540T4><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
+        else if (g.static_z) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
         else k_fft_strided<FftGeneric><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
     }
     BS_CUDA(ctx, cudaGetLastError());
