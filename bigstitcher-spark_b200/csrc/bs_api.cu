@@ -238,6 +238,15 @@ int bs_volume_free(bs_ctx* ctx, unsigned long long handle) {
     return BS_OK;
 }
 
+int bs_volume_devptr(bs_ctx* ctx, unsigned long long handle, void** dev) {
+    if (!ctx) return BS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->vols.find(handle);
+    if (it == ctx->vols.end() || !dev) return bs_set_error(ctx, BS_ERR_ARG, "bs_volume_devptr: unknown handle or NULL out");
+    *dev = it->second.dev;
+    return BS_OK;
+}
+
 int bs_volume_download(bs_ctx* ctx, unsigned long long handle, void* host) {
     if (!ctx) return BS_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);

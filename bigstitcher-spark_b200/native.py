@@ -81,7 +81,7 @@ SYMBOLS = [
     "bs_profile_enable", "bs_profile_reset", "bs_profile_get", "bs_host_alloc", "bs_host_free",
     "bs_pcm_default_params", "bs_pcm_pair", "bs_pcm_batch", "bs_good_fft_size", "bs_pcm_debug_pcm",
     "bs_fuse_default_params", "bs_volume_upload", "bs_volume_wrap", "bs_volume_free",
-    "bs_content_weights", "bs_volume_download", "bs_fuse_block", "bs_fuse_accumulate", "bs_fuse_finish",
+    "bs_content_weights", "bs_volume_download", "bs_volume_devptr", "bs_fuse_block", "bs_fuse_accumulate", "bs_fuse_finish",
 ]
 
 
@@ -124,6 +124,7 @@ def load_library():
     lib.bs_volume_free.argtypes = [vp, ull]
     lib.bs_content_weights.argtypes = [vp, ull, dbl, dbl, P(ull)]
     lib.bs_volume_download.argtypes = [vp, ull, vp]
+    lib.bs_volume_devptr.argtypes = [vp, ull, P(vp)]
     lib.bs_fuse_block.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), vp, ip]
     lib.bs_fuse_accumulate.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), vp, vp]
     lib.bs_fuse_finish.argtypes = [vp, vp, vp, ll, P(FuseParamsC), vp, ip]
@@ -293,6 +294,11 @@ class Context:
         h = C.c_ulonglong()
         self._check(self.lib.bs_volume_wrap(self.h, p, dims, dtype, C.byref(h)))
         return h.value
+
+    def volume_devptr(self, handle: int) -> int:
+        p = C.c_void_p()
+        self._check(self.lib.bs_volume_devptr(self.h, handle, C.byref(p)))
+        return int(p.value)
 
     def volume_free(self, handle: int):
         self._check(self.lib.bs_volume_free(self.h, handle))

@@ -154,6 +154,9 @@ int bs_volume_free(bs_ctx* ctx, unsigned long long handle);
 int bs_content_weights(bs_ctx* ctx, unsigned long long vol_handle, double sigma1, double sigma2,
                        unsigned long long* content_handle);
 int bs_volume_download(bs_ctx* ctx, unsigned long long handle, void* host);
+/* device address of a resident volume, so that a second context on the same device (another worker
+ * thread) can bs_volume_wrap it instead of uploading the tile twice */
+int bs_volume_devptr(bs_ctx* ctx, unsigned long long handle, void** dev);
 
 /* fuse one output block: voxel (i,j,k) is at world block_min + (i,j,k)
  * (block_min = gridBlock[0] + bbMin, J/SparkAffineFusion.java:520-534).  views must be in
