@@ -216,3 +216,86 @@ extern "C" int bs_content_weights(bs_ctx* ctx, unsigned long long vol_handle, do
     ctx->vols[*content_handle] = v;
     return BS_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Next row f-3: 2x half-pixel averaging pyramid level on the device, right after
+// fusion while the block is still resident (replaces re-reading s(l-1) from the container,
+// J/SparkAffineFusion.java:703-782; N5ApiTools.writeDownsampledBlock / LazyHalfPixelDownsample2x,
+// J/SparkDownsample.java:159-176).  One dimension after the other like the lazy upstream ops:
+// out[i] = avg(in[2i], in[2i+1]); float: 0.5f*(a+b); integer types: (a+b+1)>>1 per step.
+template <typename T>
+__device__ __forceinline__ T avg2(T a, T b);
+template <> __device__ __forceinline__ float avg2<float>(float a, float b) { return 0.5f * (a + b); }
+template <> __device__ __forceinline__ unsigned short avg2<unsigned short>(unsigned short a, unsigned short b) {
+    return (unsigned short)(((unsigned)a + (unsigned)b + 1u) >> 1);
+}
+template <> __device__ __forceinline__ unsigned char avg2<unsigned char>(unsigned char a, unsigned char b) {
+    return (unsigned char)(((unsigned)a + (unsigned)b + 1u) >> 1);
+}
+
+template <typename T>
+__global__ void k_downsample(const T* __restrict__ in, T* __restrict__ out, int dx, int dy, int dz, int ox, int oy,
+                             int oz, int fx, int fy, int fz) {
+    const long long n = (long long)ox * oy * oz;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % ox);
+        const long long r = i / ox;
+        const int y = (int)(r % oy), z = (int)(r / oy);
+        T vz[2];
+#pragma unroll
+        for (int kz = 0; kz < 2; ++kz) {
+            if (kz >= fz) { vz[kz] = vz[0]; continue; }
+            T vy[2];
+#pragma unroll
+            for (int ky = 0; ky < 2; ++ky) {
+                if (ky >= fy) { vy[ky] = vy[0]; continue; }
+                const T* p = in + ((size_t)(z * fz + kz) * dy + (y * fy + ky)) * dx + (size_t)x * fx;
+                vy[ky] = fx == 2 ? avg2<T>(p[0], p[1]) : p[0];
+            }
+            vz[kz] = fy == 2 ? avg2<T>(vy[0], vy[1]) : vy[0];
+        }
+        out[i] = fz == 2 ? avg2<T>(vz[0], vz[1]) : vz[0];
+    }
+}
+
+extern "C" int bs_downsample(bs_ctx* ctx, unsigned long long vol_handle, const int factors[3],
+                             unsigned long long* out_handle) {
+    if (!ctx) return BS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!factors || !out_handle) return bs_set_error(ctx, BS_ERR_ARG, "bs_downsample: NULL argument");
+    for (int d = 0; d < 3; ++d)
+        if (factors[d] != 1 && factors[d] != 2) return bs_set_error(ctx, BS_ERR_ARG, "bs_downsample: factors must be 1 or 2");
+    auto it = ctx->vols.find(vol_handle);
+    if (it == ctx->vols.end()) return bs_set_error(ctx, BS_ERR_ARG, "bs_downsample: unknown handle %llu", vol_handle);
+    const bs_volume src = it->second;
+    bs_volume v;
+    for (int d = 0; d < 3; ++d) {
+        v.dims[d] = src.dims[d] / factors[d];
+        if (v.dims[d] < 1) return bs_set_error(ctx, BS_ERR_ARG, "bs_downsample: dimension %d too small", d);
+    }
+    v.dtype = src.dtype;
+    v.owned = true;
+    const size_t es = src.dtype == BS_DTYPE_U16 ? 2 : src.dtype == BS_DTYPE_F32 ? 4 : 1;
+    BS_CUDA(ctx, cudaSetDevice(ctx->device));
+    BS_CUDA(ctx, cudaMalloc(&v.dev, (size_t)v.dims[0] * v.dims[1] * v.dims[2] * es));
+    const long long n = v.dims[0] * v.dims[1] * v.dims[2];
+    const int blocks = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 16);
+    {
+        bs_launch_scope sc(ctx, "downsample");
+        if (src.dtype == BS_DTYPE_U16)
+            k_downsample<unsigned short><<<blocks, 256, 0, ctx->stream>>>((const unsigned short*)src.dev, (unsigned short*)v.dev, (int)src.dims[0], (int)src.dims[1], (int)src.dims[2], (int)v.dims[0], (int)v.dims[1], (int)v.dims[2], factors[0], factors[1], factors[2]);
+        else if (src.dtype == BS_DTYPE_F32)
+            k_downsample<float><<<blocks, 256, 0, ctx->stream>>>((const float*)src.dev, (float*)v.dev, (int)src.dims[0], (int)src.dims[1], (int)src.dims[2], (int)v.dims[0], (int)v.dims[1], (int)v.dims[2], factors[0], factors[1], factors[2]);
+        else
+            k_downsample<unsigned char><<<blocks, 256, 0, ctx->stream>>>((const unsigned char*)src.dev, (unsigned char*)v.dev, (int)src.dims[0], (int)src.dims[1], (int)src.dims[2], (int)v.dims[0], (int)v.dims[1], (int)v.dims[2], factors[0], factors[1], factors[2]);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        cudaFree(v.dev);
+        return bs_set_error(ctx, BS_ERR_CUDA, "bs_downsample: %s", cudaGetErrorString(e));
+    }
+    *out_handle = ctx->next_handle++;
+    ctx->vols[*out_handle] = v;
+    return BS_OK;
+}

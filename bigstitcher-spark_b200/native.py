@@ -81,7 +81,7 @@ SYMBOLS = [
     "bs_profile_enable", "bs_profile_reset", "bs_profile_get", "bs_host_alloc", "bs_host_free",
     "bs_pcm_default_params", "bs_pcm_pair", "bs_pcm_batch", "bs_good_fft_size", "bs_pcm_debug_pcm",
     "bs_fuse_default_params", "bs_volume_upload", "bs_volume_wrap", "bs_volume_free",
-    "bs_content_weights", "bs_volume_download", "bs_volume_devptr", "bs_fuse_block", "bs_fuse_accumulate", "bs_fuse_finish",
+    "bs_content_weights", "bs_volume_download", "bs_volume_devptr", "bs_downsample", "bs_fuse_block", "bs_fuse_accumulate", "bs_fuse_finish",
 ]
 
 
@@ -125,6 +125,7 @@ def load_library():
     lib.bs_content_weights.argtypes = [vp, ull, dbl, dbl, P(ull)]
     lib.bs_volume_download.argtypes = [vp, ull, vp]
     lib.bs_volume_devptr.argtypes = [vp, ull, P(vp)]
+    lib.bs_downsample.argtypes = [vp, ull, P(ip), P(ull)]
     lib.bs_fuse_block.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), vp, ip]
     lib.bs_fuse_accumulate.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), vp, vp]
     lib.bs_fuse_finish.argtypes = [vp, vp, vp, ll, P(FuseParamsC), vp, ip]
@@ -293,6 +294,12 @@ class Context:
         dims = (C.c_longlong * 3)(*[int(v) for v in dims_xyz])
         h = C.c_ulonglong()
         self._check(self.lib.bs_volume_wrap(self.h, p, dims, dtype, C.byref(h)))
+        return h.value
+
+    def downsample(self, handle: int, factors_xyz) -> int:
+        f = (C.c_int * 3)(*[int(v) for v in factors_xyz])
+        h = C.c_ulonglong()
+        self._check(self.lib.bs_downsample(self.h, handle, f, C.byref(h)))
         return h.value
 
     def volume_devptr(self, handle: int) -> int:

@@ -154,6 +154,11 @@ int bs_volume_free(bs_ctx* ctx, unsigned long long handle);
 int bs_content_weights(bs_ctx* ctx, unsigned long long vol_handle, double sigma1, double sigma2,
                        unsigned long long* content_handle);
 int bs_volume_download(bs_ctx* ctx, unsigned long long handle, void* host);
+/* next row 8f-3: one 2x half-pixel averaging pyramid step on a resident volume (factors 1 or 2 per
+ * axis, output dims = floor(dims / factors), same dtype) -> new handle.  Replaces re-reading level
+ * l-1 from the container for every pyramid level (J/SparkAffineFusion.java:703-782). */
+int bs_downsample(bs_ctx* ctx, unsigned long long vol_handle, const int factors[3],
+                  unsigned long long* out_handle);
 /* device address of a resident volume, so that a second context on the same device (another worker
  * thread) can bs_volume_wrap it instead of uploading the tile twice */
 int bs_volume_devptr(bs_ctx* ctx, unsigned long long handle, void** dev);

@@ -307,3 +307,21 @@ def convert_output(out, out_dtype, min_intensity, max_intensity):
     a = np.floor(a + 0.5)
     a = np.clip(a, 0, top)
     return a.astype(np.uint8 if top == 255.0 else np.uint16)
+
+
+def downsample2x(vol, factors_xyz):
+    """One pyramid step (N5ApiTools.writeDownsampledBlock / LazyHalfPixelDownsample2x restated; next
+    row 8f-3): per axis with factor 2, out[i] = avg(in[2i], in[2i+1]), x then y then z; float32:
+    0.5*(a+b); integer types: (a+b+1)>>1 per step (rounding rule recalled, PARITY_GAPS #23)."""
+    out = vol
+    for ax, f in zip((2, 1, 0), factors_xyz):
+        if f == 1:
+            continue
+        n = out.shape[ax] // 2
+        a = np.take(out, np.arange(0, 2 * n, 2), axis=ax)
+        b = np.take(out, np.arange(1, 2 * n, 2), axis=ax)
+        if out.dtype == np.float32:
+            out = (np.float32(0.5) * (a + b)).astype(np.float32)
+        else:
+            out = ((a.astype(np.uint32) + b.astype(np.uint32) + 1) >> 1).astype(vol.dtype)
+    return out

@@ -237,3 +237,17 @@ def test_bad_arguments(ctx):
         ctx.fuse_block([dict(src_to_world=np.eye(3, 4), vol_handle=h)], (0, 0, 0), (4, 4, 4),
                        ctx.fuse_params(fusion_type=99))
     ctx.volume_free(h)
+
+
+@pytest.mark.parametrize("dtype", [np.uint16, np.float32, np.uint8])
+@pytest.mark.parametrize("factors", [(2, 2, 1), (2, 2, 2), (1, 1, 2)])
+def test_device_pyramid_step_bit_exact(ctx, dtype, factors):
+    rng = np.random.default_rng(3)
+    vol = (rng.random((21, 34, 45)) * 250).astype(dtype)
+    h = ctx.volume_upload(vol)
+    h2 = ctx.downsample(h, factors)
+    want = fo.downsample2x(vol, factors)
+    got = ctx.volume_download(h2, want.shape[::-1], dtype)
+    assert np.array_equal(got, want)
+    ctx.volume_free(h)
+    ctx.volume_free(h2)

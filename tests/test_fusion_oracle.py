@@ -128,3 +128,11 @@ def test_golden_fusion_block():
     want = np.load(GOLDEN)["avg_blend"]
     got = make_golden.fusion_case()
     assert np.array_equal(got, want)
+
+
+def test_downsample_known_answers():
+    v = np.arange(2 * 2 * 4, dtype=np.float32).reshape(2, 2, 4)
+    assert np.array_equal(fo.downsample2x(v, (2, 1, 1)), [[[0.5, 2.5], [4.5, 6.5]], [[8.5, 10.5], [12.5, 14.5]]])
+    assert fo.downsample2x(v, (2, 2, 2)).shape == (1, 1, 2) and fo.downsample2x(v, (2, 2, 2))[0, 0, 0] == 6.5
+    u = np.array([[[1, 2, 3, 4, 9]]], dtype=np.uint16)
+    assert list(fo.downsample2x(u, (2, 1, 1)).ravel()) == [2, 4]    # (1+2+1)>>1, (3+4+1)>>1, odd tail dropped
