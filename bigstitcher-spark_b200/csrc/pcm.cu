@@ -898,6 +898,7 @@ typedef FftStatic<270, 4, 17, 2, PCM_THREADS, 9, 6, 5> FftX270;
 typedef FftStatic<270, 3, 9, 2, PCM_THREADS, 9, 6, 5> FftX270L8;
 typedef FftStatic<540, 3, 8, 1, PCM_THREADS, 9, 10, 6> FftS540;
 typedef FftStatic<540, 2, 4, 1, PCM_THREADS, 9, 10, 6> FftS540T4;
+typedef FftStatic<540, 3, 8, 1, PCM_THREADS, 27, 20> FftS540R2;   // two-stage variant (radix 27 x 20)
 
 struct GatherArgs {
     const float* pcm;
@@ -1351,7 +1352,9 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftX270L8>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_strided<FftS540>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_strided<FftS540T4>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_strided<FftS540R2>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_strided_pipe<FftS540>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_strided_pipe<FftS540R2>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_strided_pipe<FftGeneric>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftX270>, 0))) return rc;
         ctx->pcm_attr_done = true;
@@ -1433,7 +1436,8 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
             pp.n_tiles = pp.tiles_x * pp.n_other * 2;
             const int per_sm = std::max(1, std::min(2, (int)(PCM_SMEM_MAX / (smem_pipe + 1024))));
             const int nctas = std::min(pp.n_tiles, ctx->sm_count * per_sm);
-            if (g.static_y) k_fft_strided_pipe<FftS540><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
+            if (g.static_y && env_int("BS_FFT_Y_R2", 0)) k_fft_strided_pipe<FftS540R2><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
+            else if (g.static_y) k_fft_strided_pipe<FftS540><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
             else k_fft_strided_pipe<FftGeneric><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
         } else if (g.static_y) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
         else k_fft_strided<FftGeneric><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
@@ -1451,7 +1455,8 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         a.thresh = 1e-5f;  // PhaseCorrelation2Util.normalizeInterval threshold
         dim3 grid(g.pitch >> g.tshift_z, g.P[1], 1);
         bs_launch_scope sc(ctx, "fft_z_xpower");
-        if (g.static_z && g.tshift_z == 2) k_fft_strided<FftS540T4><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
+        if (g.static_z && g.tshift_z == 3 && env_int("BS_FFT_Z_R2", 1)) k_fft_strided<FftS540R2><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
+        else if (g.static_z && g.tshift_z == 2) k_fft_strided<FftS540T4><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
         else if (g.static_z) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
         else k_fft_strided<FftGeneric><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
     }
@@ -1477,7 +1482,8 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
             pp.n_tiles = pp.tiles_x * pp.n_other * 1;
             const int per_sm = std::max(1, std::min(2, (int)(PCM_SMEM_MAX / (smem_pipe + 1024))));
             const int nctas = std::min(pp.n_tiles, ctx->sm_count * per_sm);
-            if (g.static_y) k_fft_strided_pipe<FftS540><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
+            if (g.static_y && env_int("BS_FFT_Y_R2", 0)) k_fft_strided_pipe<FftS540R2><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
+            else if (g.static_y) k_fft_strided_pipe<FftS540><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
             else k_fft_strided_pipe<FftGeneric><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
         } else if (g.static_y) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
         else k_fft_strided<FftGeneric><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
