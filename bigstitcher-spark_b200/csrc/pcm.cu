@@ -1436,7 +1436,7 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
             pp.n_tiles = pp.tiles_x * pp.n_other * 2;
             const int per_sm = std::max(1, std::min(2, (int)(PCM_SMEM_MAX / (smem_pipe + 1024))));
             const int nctas = std::min(pp.n_tiles, ctx->sm_count * per_sm);
-            if (g.static_y && env_int("BS_FFT_Y_R2", 0)) k_fft_strided_pipe<FftS540R2><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
+            if (g.static_y && env_int("BS_FFT_Y_R2", 1)) k_fft_strided_pipe<FftS540R2><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
             else if (g.static_y) k_fft_strided_pipe<FftS540><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
             else k_fft_strided_pipe<FftGeneric><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
         } else if (g.static_y) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
@@ -1482,7 +1482,7 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
             pp.n_tiles = pp.tiles_x * pp.n_other * 1;
             const int per_sm = std::max(1, std::min(2, (int)(PCM_SMEM_MAX / (smem_pipe + 1024))));
             const int nctas = std::min(pp.n_tiles, ctx->sm_count * per_sm);
-            if (g.static_y && env_int("BS_FFT_Y_R2", 0)) k_fft_strided_pipe<FftS540R2><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
+            if (g.static_y && env_int("BS_FFT_Y_R2", 1)) k_fft_strided_pipe<FftS540R2><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
             else if (g.static_y) k_fft_strided_pipe<FftS540><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
             else k_fft_strided_pipe<FftGeneric><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
         } else if (g.static_y) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
