@@ -136,8 +136,9 @@ def cpu_pcm_sample(n, procs, threads, repeats=1):
     """Time the oracle port on `procs` concurrent pairs (the reference runs one single-threaded
     task per Spark executor slot, J/SparkPairwiseStitching.java:210); returns pairs/s."""
     from tests import synth
-    a, b = synth.shifted_pair((n, n, n), (7, -5, 3), seed=99, margin=12, sigma=2.0)
-    _CPU["a"], _CPU["b"] = a, b
+    if _CPU.get("n") != n:   # generate the sample pair once per process
+        _CPU["a"], _CPU["b"] = synth.shifted_pair((n, n, n), (7, -5, 3), seed=99, margin=12, sigma=2.0)
+        _CPU["n"] = n
     ctxm = mp.get_context("fork")
     times = []
     with ctxm.Pool(procs) as pool:
@@ -202,8 +203,10 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * procs / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"phase-correlation, {n}^3 uint16 overlap crops, P=5-smooth pad, peaks=5, subpixel",
-                   "note": "Java reference not runnable in this image; CPU arm = numpy/scipy oracle port"},
+        "config": {"workload": f"phase-correlation: bounded sample of the {n}^3 uint16 overlap-crop workload "
+                               f"(BASELINE configs[1]), 5-smooth pad, peaks=5, subpixel, minOverlap 0.25",
+                   "note": "Java reference not runnable in this image (no JVM; arithmetic in un-vendored Maven "
+                           "artefacts); CPU arm = numpy/scipy-pocketfft oracle port on the host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs * threads, "host_cores": ncores,
                          "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -119,3 +119,21 @@ def test_bad_arguments(ctx):
         ctx.pcm_pair(a, a, ctx.pcm_params(peaks_to_check=0))
     with pytest.raises(bsgpu.BsError):
         ctx.pcm_pair(a, a, ctx.pcm_params(peaks_to_check=1000))
+
+
+def test_mixed_size_batch_regrows_workspace(ctx):
+    """Pairs of different sizes in one call: workspace, twiddle tables and profiles are rebuilt per size."""
+    specs = [((40, 48, 56), (2, -1, 3)), ((64, 64, 64), (-3, 4, 1)), ((33, 45, 71), (1, 1, -2)), ((40, 48, 56), (0, 5, -4))]
+    pairs = [synth.shifted_pair(sh, s, seed=60 + i) for i, (sh, s) in enumerate(specs)]
+    batch = ctx.pcm_batch([p[0] for p in pairs], [p[1] for p in pairs])
+    for (sh, s), r, (a, b) in zip(specs, batch, pairs):
+        o = po.pcm_shift(a, b)
+        assert r.found and r.shift_int == o.shift_int == s and r.pad == o.pad
+        assert np.allclose(r.shift_sub, o.shift_sub, atol=1e-3) and abs(r.r - o.r) < 1e-9
+
+
+def test_large_single_axis_generic_path(ctx):
+    """A long, thin crop (x pad 810 = 2*3^4*5, M = 405 > 319): CTA-level x kernels + generic plans."""
+    a, b = synth.shifted_pair((12, 20, 780), (9, -2, 1), seed=70, margin=12)
+    g, o = _check(ctx, a, b)
+    assert g.shift_int == (9, -2, 1)
