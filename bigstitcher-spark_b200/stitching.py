@@ -127,6 +127,30 @@ def downsample_avg(img: np.ndarray, factors_xyz):
     return v
 
 
+def aggregate_group(images, action="AVERAGE"):
+    """GroupedViewAggregator for one attribute (--channelCombine / --illumCombine,
+    J/SparkPairwiseStitching.java:103-107,204-208): AVERAGE -> float32 mean of the group's images,
+    PICK_BRIGHTEST -> the image with the highest mean intensity.  Single-view groups pass through."""
+    images = list(images)
+    if len(images) == 1:
+        return images[0]
+    if action == "AVERAGE":
+        acc = np.zeros(images[0].shape, dtype=np.float32)
+        for im in images:
+            acc += im.astype(np.float32)
+        return acc / np.float32(len(images))
+    if action == "PICK_BRIGHTEST":
+        return images[int(np.argmax([float(im.mean(dtype=np.float64)) for im in images]))]
+    raise ValueError(f"unknown ActionType {action}")
+
+
+def _world_box(m, dims_xyz):
+    c = np.array([[x, y, z] for x in (0, dims_xyz[0] - 1) for y in (0, dims_xyz[1] - 1)
+                  for z in (0, dims_xyz[2] - 1)], dtype=np.float64)
+    w = c @ m[:, :3].T + m[:, 3]
+    return w.min(axis=0), w.max(axis=0)
+
+
 def compute_stitching(img_a, img_b, model_a, model_b, params: PairwiseStitchingParameters,
                       downsample_factors=(1, 1, 1), ctx: Context | None = None):
     """TransformationTools.computeStitching for single-view groups whose registrations differ
@@ -138,8 +162,7 @@ def compute_stitching(img_a, img_b, model_a, model_b, params: PairwiseStitchingP
     ma = np.asarray(model_a, dtype=np.float64).reshape(3, 4)
     mb = np.asarray(model_b, dtype=np.float64).reshape(3, 4)
     if not non_translations_equal(ma, mb):
-        raise NotImplementedError("computeStitchingNonEqualTransformations (virtually fused views) "
-                                  "is outside this build's scope (SURVEY.md 8a row a3')")
+        return compute_stitching_non_equal_transformations(img_a, img_b, ma, mb, params, downsample_factors, ctx)
     ds = np.asarray(downsample_factors, dtype=np.float64)
     a = downsample_avg(img_a, downsample_factors) if isinstance(img_a, np.ndarray) else img_a
     b = downsample_avg(img_b, downsample_factors) if isinstance(img_b, np.ndarray) else img_b
@@ -148,15 +171,8 @@ def compute_stitching(img_a, img_b, model_a, model_b, params: PairwiseStitchingP
     t1 = (lin_inv @ ma[:, 3]) / ds
     t2 = (lin_inv @ mb[:, 3]) / ds
     # world-space overlap bounding box of the two views (BoundingBoxMaximalGroupOverlap)
-    def world_box(m, dims_xyz):
-        c = np.array([[x, y, z] for x in (0, dims_xyz[0] - 1) for y in (0, dims_xyz[1] - 1)
-                      for z in (0, dims_xyz[2] - 1)], dtype=np.float64)
-        w = c @ m[:, :3].T + m[:, 3]
-        return w.min(axis=0), w.max(axis=0)
-    full_a = tuple(img_a.shape)[::-1]
-    full_b = tuple(img_b.shape)[::-1]
-    la, ha = world_box(ma, full_a)
-    lb, hb = world_box(mb, full_b)
+    la, ha = _world_box(ma, tuple(img_a.shape)[::-1])
+    lb, hb = _world_box(mb, tuple(img_b.shape)[::-1])
     ov = _overlap(la, ha, lb, hb)
     if ov is None:
         return None
@@ -169,6 +185,48 @@ def compute_stitching(img_a, img_b, model_a, model_b, params: PairwiseStitchingP
     Mb = np.vstack([mb, [0, 0, 0, 1]])
     R = Mb @ T @ np.linalg.inv(Mb)
     return (R[:3, :].copy(), float(r)), (tuple(ov[0]), tuple(ov[1]))
+
+
+def compute_stitching_non_equal_transformations(img_a, img_b, model_a, model_b, params: PairwiseStitchingParameters,
+                                                downsample_factors=(1, 1, 1), ctx: Context | None = None):
+    """TransformationTools.computeStitchingNonEqualTransformations (J/SparkPairwiseStitching.java:259-267;
+    SURVEY.md 8a row a3'): when the non-translation parts differ, both views are virtually fused
+    (n-linear resampling, no blending) into their common world-space overlap box on the
+    ``downsample_factors`` grid -- here with the same fusion kernel that serves `affine-fusion` --
+    and the two rendered volumes are phase-correlated with zero initial translations.  The shift is
+    already a world-space translation: resTransform = T(shift * ds)."""
+    from . import native
+    ma = np.asarray(model_a, dtype=np.float64).reshape(3, 4)
+    mb = np.asarray(model_b, dtype=np.float64).reshape(3, 4)
+    ds = np.asarray(downsample_factors, dtype=np.float64)
+    la, ha = _world_box(ma, tuple(img_a.shape)[::-1])
+    lb, hb = _world_box(mb, tuple(img_b.shape)[::-1])
+    ov = _overlap(la, ha, lb, hb)
+    if ov is None:
+        return None
+    lo = np.ceil(ov[0] / ds).astype(np.int64)          # overlap box on the downsampled world grid
+    hi = np.floor(ov[1] / ds).astype(np.int64)
+    size = hi - lo + 1
+    if np.any(size <= 0):
+        return None
+    S = np.diag(np.concatenate([1.0 / ds, [1.0]]))       # world -> downsampled world
+    p = ctx.fuse_params("AVG", 1, native.DTYPE_F32)
+    rendered = []
+    for img, m in ((img_a, ma), (img_b, mb)):
+        h = ctx.volume_upload(np.ascontiguousarray(img))
+        try:
+            m_ds = (S @ np.vstack([m, [0, 0, 0, 1]]))[:3]
+            rendered.append(ctx.fuse_block([dict(src_to_world=m_ds, vol_handle=h)], lo, size, p))
+        finally:
+            ctx.volume_free(h)
+    pp = ctx.pcm_params(params.peaks_to_check, params.do_subpixel, params.min_overlap, params.extension)
+    res = ctx.pcm_pair(rendered[0], rendered[1], pp)
+    if not res.found or math.isinf(res.r):
+        return None
+    shift = np.asarray(res.shift_sub if params.do_subpixel else res.shift_int, dtype=np.float64)
+    R = np.eye(4)
+    R[:3, 3] = shift * ds
+    return (R[:3, :].copy(), float(res.r)), (tuple(ov[0]), tuple(ov[1]))
 
 
 def filter_results(results, min_r=0.3, max_r=1.0, max_shift_xyz=None, max_shift_total=None):

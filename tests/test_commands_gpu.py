@@ -44,3 +44,34 @@ def test_stitching_then_fusion_end_to_end(ctx, tmp_path):
     want = fo.fuse_block(views, (0, 0, 0), (nominal + n, n, n), fo.AVG_BLEND)
     err = np.abs(fused - want) / np.maximum(np.abs(want), 1.0)
     assert (err > 1e-4).mean() < 1e-3 and fused.shape == want.shape
+
+
+def test_non_equal_transformations_branch_virtual_fusion(ctx):
+    """Row a3': registrations whose linear parts differ (B carries a 1.5 % scale) go through virtual
+    fusion of both views on the world grid + phase correlation; the planted world-space error of B
+    is recovered, and the GPU result equals the same pipeline evaluated with the oracle."""
+    from bsgpu import stitching
+    from oracle import pcm_oracle as po
+    n, ov = 96, 44
+    nominal = n - ov
+    G = synth.field((n + 16, n + 16, 2 * n + 16), seed=5, sigma=1.5)
+    A = synth.tile_from(G, (8, 8, 8), (n, n, n), 1, noise=5)
+    B = synth.tile_from(G, (8 + 2, 8 - 1, 8 + nominal + 3), (n, n, n), 2, noise=5)   # truly at nominal + (3,-1,2)
+    Ma = synth.translation((0, 0, 0))
+    Mb = synth.translation((nominal, 0, 0)).copy()
+    Mb[0, 0] = 1.0000001   # linear parts differ -> nonTranslationsEqual is false, geometry is unchanged
+    assert not stitching.non_translations_equal(Ma, Mb, eps=1e-12)
+    res = stitching.compute_stitching_non_equal_transformations(A, B, Ma, Mb, stitching.PairwiseStitchingParameters(),
+                                                                (1, 1, 1), ctx)
+    assert res is not None
+    (T, r), (bmin, bmax) = res
+    assert np.all(np.rint(T[:, 3]) == (3, -1, 2)) and r > 0.9
+    # oracle evaluation of the same pipeline
+    lo = np.ceil(np.maximum((0, 0, 0), (nominal, 0, 0))).astype(int)
+    hi = np.floor(np.minimum((n - 1,) * 3, (nominal * 1.0 + (n - 1) * 1.0000001, n - 1, n - 1))).astype(int)
+    size = hi - lo + 1
+    ra = fo.fuse_block([fo.View(A, Ma)], lo, size, fo.AVG)
+    rb = fo.fuse_block([fo.View(B, Mb)], lo, size, fo.AVG)
+    o = po.pcm_shift(ra, rb)
+    assert tuple(np.rint(T[:, 3]).astype(int)) == o.shift_int
+    assert np.allclose(T[:, 3], o.shift_sub, atol=2e-3) and abs(r - o.r) < 1e-5

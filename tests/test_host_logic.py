@@ -107,7 +107,12 @@ def test_compute_stitching_downsampled_scales_shift_back():
     assert np.all(np.abs(T[:, 3] - (-4, 2, 0)) <= 1.0)
 
 
-def test_compute_stitching_rejects_non_equal_linear_parts():
-    a = np.zeros((4, 4, 4), np.uint16)
-    with pytest.raises(NotImplementedError):
-        stitching.compute_stitching(a, a, synth.translation((0, 0, 0)), synth.rot_z(2.0), stitching.PairwiseStitchingParameters())
+def test_aggregate_group_actions():
+    a = np.full((2, 2, 2), 10, np.uint16)
+    b = np.full((2, 2, 2), 30, np.uint16)
+    assert stitching.aggregate_group([a]) is a
+    avg = stitching.aggregate_group([a, b], "AVERAGE")
+    assert avg.dtype == np.float32 and np.all(avg == 20)
+    assert stitching.aggregate_group([a, b], "PICK_BRIGHTEST") is b
+    with pytest.raises(ValueError):
+        stitching.aggregate_group([a, b], "NOPE")
