@@ -54,7 +54,7 @@ def test_non_equal_transformations_branch_virtual_fusion(ctx):
     from oracle import pcm_oracle as po
     n, ov = 96, 44
     nominal = n - ov
-    G = synth.field((n + 16, n + 16, 2 * n + 16), seed=5, sigma=1.5)
+    G = synth.field((n + 16, n + 16, 2 * n + 16), seed=5, sigma=1.0)
     A = synth.tile_from(G, (8, 8, 8), (n, n, n), 1, noise=5)
     B = synth.tile_from(G, (8 + 2, 8 - 1, 8 + nominal + 3), (n, n, n), 2, noise=5)   # truly at nominal + (3,-1,2)
     Ma = synth.translation((0, 0, 0))
