@@ -6,5 +6,5 @@ top-level alias module ``bsgpu`` (``import bsgpu``).  The compute path is
 ``libbsgpu.so`` (hand-written CUDA behind the C ABI in ``include/bsgpu.h``); nothing here
 falls back to the CPU.
 """
-from . import native, stitching, fusion, parallel, n5, spimdata, commands  # noqa: F401
+from . import native, stitching, fusion, parallel, n5, zarr, spimdata, commands  # noqa: F401
 from .native import BsError, Context, load_library, good_fft_size  # noqa: F401

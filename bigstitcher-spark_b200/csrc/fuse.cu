@@ -698,6 +698,39 @@ int bs_fuse_block(bs_ctx* ctx, const bs_view* views, int n_views, const long lon
     return BS_OK;
 }
 
+int bs_fuse_block_to_volume(bs_ctx* ctx, const bs_view* views, int n_views, const long long block_min[3],
+                            const long long block_size[3], const bs_fuse_params* params, unsigned long long* out_handle) {
+    if (!ctx) return BS_ERR_ARG;
+    if (!out_handle || !block_size || !params) return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse_block_to_volume: NULL argument");
+    void* dev = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        for (int d = 0; d < 3; ++d)
+            if (block_size[d] <= 0 || block_size[d] > 0x7fffffffLL)
+                return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse_block_to_volume: bad block_size");
+        BS_CUDA(ctx, cudaSetDevice(ctx->device));
+        BS_CUDA(ctx, cudaMalloc(&dev, (size_t)block_size[0] * block_size[1] * block_size[2] * out_elem_size(params->out_dtype)));
+    }
+    int rc = bs_fuse_block(ctx, views, n_views, block_min, block_size, params, dev, 1);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (rc == BS_OK) {
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) rc = bs_set_error(ctx, BS_ERR_CUDA, "bs_fuse_block_to_volume: %s", cudaGetErrorString(e));
+    }
+    if (rc != BS_OK) {
+        cudaFree(dev);
+        return rc;
+    }
+    bs_volume v;
+    v.dev = dev;
+    v.dims[0] = block_size[0]; v.dims[1] = block_size[1]; v.dims[2] = block_size[2];
+    v.dtype = params->out_dtype;
+    v.owned = true;
+    *out_handle = ctx->next_handle++;
+    ctx->vols[*out_handle] = v;
+    return BS_OK;
+}
+
 int bs_fuse_accumulate(bs_ctx* ctx, const bs_view* views, int n_views, const long long block_min[3],
                        const long long block_size[3], const bs_fuse_params* params, float* sum_wi_dev,
                        float* sum_w_dev) {

@@ -157,6 +157,16 @@ class BlockSupplier:
                                       self.min_intensity, self.max_intensity)
         return self.ctx.fuse_block(self.views_for(vids), wmin, size, params, out=out)
 
+    def copy_to_volume(self, interval_min, interval_max) -> int:
+        """Like copy(), but the block stays on the device: returns a resident-volume handle."""
+        imin = np.asarray(interval_min, dtype=np.int64)
+        size = np.asarray(interval_max, dtype=np.int64) - imin + 1
+        wmin = imin + np.asarray(self.bb_min, dtype=np.int64)
+        vids = find_overlapping_views(self.view_dims, self.registrations, wmin, wmin + size - 1, self.view_ids)
+        params = self.ctx.fuse_params(self.fusion_type, self.interpolation, self.out_dtype, self.blend_lut_n,
+                                      self.min_intensity, self.max_intensity)
+        return self.ctx.fuse_block_to_volume(self.views_for(vids), wmin, size, params)
+
 
 class BlkAffineFusion:
     """net.preibisch.mvrecon.process.fusion.blk.BlkAffineFusion (call site

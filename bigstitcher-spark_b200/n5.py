@@ -177,7 +177,7 @@ def write_bdv_setup(store: N5Store, setup: int, timepoint: int, volume: np.ndarr
 
 def create_fusion_container(root, input_xml, bb_min, bb_max, block_size=(128, 128, 128), dtype="float32",
                             min_intensity=None, max_intensity=None, num_timepoints=1, num_channels=1,
-                            anisotropy_factor=None, compression="raw"):
+                            anisotropy_factor=None, compression="raw", downsamplings=()):
     """`create-fusion-container -s N5` (J/CreateFusionContainer.java:302-320,490-519): per
     (channel, timepoint) dataset `ch{c}tp{t}/s0` plus the `Bigstitcher-Spark/*` root attributes
     that `affine-fusion` reads back (J/SparkAffineFusion.java:241-307)."""
@@ -188,8 +188,20 @@ def create_fusion_container(root, input_xml, bb_min, bb_max, block_size=(128, 12
         for c in range(num_channels):
             ds = f"ch{c}tp{t}/s0"
             store.create_dataset(ds, dims, block_size, _DTYPES[dtype], compression)
-            mr.append([{"dataset": ds, "dimensions": dims, "blockSize": list(block_size),
-                        "relativeDownsampling": [1, 1, 1], "absoluteDownsampling": [1, 1, 1], "dataType": dtype}])
+            levels = [{"dataset": ds, "dimensions": dims, "blockSize": list(block_size),
+                       "relativeDownsampling": [1, 1, 1], "absoluteDownsampling": [1, 1, 1], "dataType": dtype}]
+            # --multiRes: s1, s2, ... with relative 2x steps (N5ApiTools.setupMultiResolutionPyramid,
+            # J/CreateFusionContainer.java:260-270)
+            cur, absd = list(dims), [1, 1, 1]
+            for lvl, rel in enumerate(downsamplings, start=1):
+                cur = [cur[d] // int(rel[d]) for d in range(3)]
+                absd = [absd[d] * int(rel[d]) for d in range(3)]
+                dsl = f"ch{c}tp{t}/s{lvl}"
+                store.create_dataset(dsl, cur, block_size, _DTYPES[dtype], compression)
+                levels.append({"dataset": dsl, "dimensions": list(cur), "blockSize": list(block_size),
+                               "relativeDownsampling": [int(v) for v in rel], "absoluteDownsampling": list(absd),
+                               "dataType": dtype})
+            mr.append(levels)
     attrs = {"Bigstitcher-Spark/FusionFormat": "N5", "Bigstitcher-Spark/InputXML": input_xml,
              "Bigstitcher-Spark/NumTimepoints": num_timepoints, "Bigstitcher-Spark/NumChannels": num_channels,
              "Bigstitcher-Spark/Boundingbox_min": [int(v) for v in bb_min],

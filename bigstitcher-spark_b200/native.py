@@ -81,7 +81,7 @@ SYMBOLS = [
     "bs_profile_enable", "bs_profile_reset", "bs_profile_get", "bs_host_alloc", "bs_host_free",
     "bs_pcm_default_params", "bs_pcm_pair", "bs_pcm_batch", "bs_good_fft_size", "bs_pcm_debug_pcm",
     "bs_fuse_default_params", "bs_volume_upload", "bs_volume_wrap", "bs_volume_free",
-    "bs_content_weights", "bs_volume_download", "bs_volume_devptr", "bs_downsample", "bs_fuse_block", "bs_fuse_accumulate", "bs_fuse_finish",
+    "bs_content_weights", "bs_volume_download", "bs_volume_devptr", "bs_downsample", "bs_fuse_block", "bs_fuse_block_to_volume", "bs_fuse_accumulate", "bs_fuse_finish",
 ]
 
 
@@ -127,6 +127,7 @@ def load_library():
     lib.bs_volume_devptr.argtypes = [vp, ull, P(vp)]
     lib.bs_downsample.argtypes = [vp, ull, P(ip), P(ull)]
     lib.bs_fuse_block.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), vp, ip]
+    lib.bs_fuse_block_to_volume.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), P(ull)]
     lib.bs_fuse_accumulate.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), vp, vp]
     lib.bs_fuse_finish.argtypes = [vp, vp, vp, ll, P(FuseParamsC), vp, ip]
     _lib = lib
@@ -358,6 +359,16 @@ class Context:
         p, on_dev, _ = _ptr_of(out)
         self._check(self.lib.bs_fuse_block(self.h, arr, n, bmin, bsz, C.byref(params), p, 1 if on_dev else 0))
         return out
+
+    def fuse_block_to_volume(self, views, block_min_xyz, block_size_xyz, params: FuseParamsC | None = None) -> int:
+        """Fuse one block into a new resident volume; returns its handle."""
+        params = params or self.fuse_params()
+        arr, n = views if isinstance(views, tuple) else self.make_views(views)
+        bmin = (C.c_longlong * 3)(*[int(v) for v in block_min_xyz])
+        bsz = (C.c_longlong * 3)(*[int(v) for v in block_size_xyz])
+        h = C.c_ulonglong()
+        self._check(self.lib.bs_fuse_block_to_volume(self.h, arr, n, bmin, bsz, C.byref(params), C.byref(h)))
+        return h.value
 
     def fuse_accumulate(self, views, block_min_xyz, block_size_xyz, params, sum_wi, sum_w):
         arr, n = views if isinstance(views, tuple) else self.make_views(views)

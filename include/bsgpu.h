@@ -171,6 +171,12 @@ int bs_fuse_block(bs_ctx* ctx, const bs_view* views, int n_views, const long lon
                   const long long block_size[3], const bs_fuse_params* params,
                   void* out, int out_on_device);
 
+/* same, but the fused block stays on the device as a new resident volume (handle): the pyramid
+ * levels are then derived with bs_downsample before anything is downloaded (next row 8f-3) */
+int bs_fuse_block_to_volume(bs_ctx* ctx, const bs_view* views, int n_views, const long long block_min[3],
+                            const long long block_size[3], const bs_fuse_params* params,
+                            unsigned long long* out_handle);
+
 /* view-sharded mode: accumulate this context's views into partial sums
  * sum_wi / sum_w (device float32, block_size elements each, NOT cleared), to be all-reduced
  * across devices by the caller (NCCL) and finished with bs_fuse_finish. */

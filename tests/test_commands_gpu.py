@@ -45,6 +45,28 @@ def test_stitching_then_fusion_end_to_end(ctx, tmp_path):
     err = np.abs(fused - want) / np.maximum(np.abs(want), 1.0)
     assert (err > 1e-4).mean() < 1e-3 and fused.shape == want.shape
 
+    # --multiRes: pyramid levels derived on the device from the resident fused block
+    outm = str(tmp_path / "fused_mr.n5")
+    commands.create_fusion_container(xml, outm, block_size=(32, 32, 32), downsamplings=[(2, 2, 1), (2, 2, 2)])
+    commands.affine_fusion(outm, ctx, "AVG_BLEND", block_scale=(2, 2, 2))
+    stm, mm = bn5.read_fusion_container(outm)
+    lv = mm["mr_infos"][0]
+    assert [l["dataset"] for l in lv] == ["ch0tp0/s0", "ch0tp0/s1", "ch0tp0/s2"]
+    s0 = stm.read_volume("ch0tp0/s0")
+    assert np.array_equal(s0, fused)
+    s1 = fo.downsample2x(s0, (2, 2, 1))
+    assert np.array_equal(stm.read_volume("ch0tp0/s1"), s1)
+    assert np.array_equal(stm.read_volume("ch0tp0/s2"), fo.downsample2x(s1, (2, 2, 2)))
+
+    # the reference's default container: OME-ZARR 5-D, guessed from the extension
+    from bsgpu import zarr as bz
+    outz = str(tmp_path / "fused.zarr")
+    commands.create_fusion_container(xml, outz, block_size=(32, 32, 32))
+    dz = commands.affine_fusion(outz, ctx, "AVG_BLEND", block_scale=(2, 2, 1))
+    stz, mz = bz.read_fusion_container_zarr(outz)
+    assert mz["format"] == "OME-ZARR" and dz == "0"
+    assert np.array_equal(stz.read_volume("0"), fused)
+
 
 def test_non_equal_transformations_branch_virtual_fusion(ctx):
     """Row a3': registrations whose linear parts differ (B carries a 1.5 % scale) go through virtual

@@ -104,3 +104,35 @@ def test_stitching_results_written_replaced_and_reloaded(tmp_path):
     h1 = spimdata.SpimData2.transform_hash(d.registrations[(0, 0)], d.registrations[(0, 1)])
     h2 = spimdata.SpimData2.transform_hash(d.registrations[(0, 0)], d.registrations[(0, 2)])
     assert h1 != h2
+
+
+def test_zarr_chunk_layout_known_answer(tmp_path):
+    from bsgpu import zarr as bz
+    st = bz.ZarrStore(str(tmp_path / "f.zarr"), create=True)
+    st.create_array("0", (2, 3, 5, 6, 7), (1, 1, 4, 4, 4), "uint16")
+    blk = (np.arange(5 * 6 * 7, dtype=np.uint16).reshape(5, 6, 7) + 1)
+    st.save_block("0", blk, (0, 0, 0, 2, 1))          # channel 2, timepoint 1
+    # chunk files live at t/c/z/y/x with "/" separator; every chunk has the full 4x4x4 shape, little-endian
+    p = tmp_path / "f.zarr" / "0" / "1" / "2" / "1" / "1" / "1"
+    raw = np.frombuffer(open(p, "rb").read(), dtype="<u2").reshape(4, 4, 4)
+    assert raw[0, 0, 0] == blk[4, 4, 4] and raw[0, 0, 3] == 0 and raw[1].max() == 0   # edge chunk zero-padded
+    assert np.array_equal(st.read_volume("0", c=2, t=1), blk)
+    assert not st.read_volume("0", c=0, t=0).any()
+    meta = st.array_meta("0")
+    assert meta["shape"] == [2, 3, 5, 6, 7] and meta["chunks"] == [1, 1, 4, 4, 4] and meta["dtype"] == "<u2"
+    assert meta["dimension_separator"] == "/" and meta["order"] == "C" and meta["compressor"] is None
+
+
+def test_zarr_fusion_container_contract_and_gzip(tmp_path):
+    from bsgpu import zarr as bz
+    st = bz.create_fusion_container_zarr(str(tmp_path / "o.zarr"), "/d/dataset.xml", (0, 0, 0), (49, 39, 29), (16, 16, 16),
+                                         "float32", compression="gzip")
+    vol = np.random.default_rng(2).random((30, 40, 50)).astype(np.float32)
+    st.save_block("0", vol[:16, :32, :32], (0, 0, 0, 0, 0))
+    st.save_block("0", vol[:16, :32, 32:], (2, 0, 0, 0, 0))
+    st2, m = bz.read_fusion_container_zarr(str(tmp_path / "o.zarr"))
+    assert m["format"] == "OME-ZARR" and m["bb_max"] == [49, 39, 29] and m["block_size"] == [16, 16, 16]
+    back = st2.read_volume("0")
+    assert np.array_equal(back[:16, :32, :], vol[:16, :32, :]) and not back[16:].any()
+    ms = st2.get_attributes("")["multiscales"][0]
+    assert [a["name"] for a in ms["axes"]] == ["t", "c", "z", "y", "x"] and ms["datasets"][0]["path"] == "0"
