@@ -129,12 +129,10 @@ def affine_fusion(out_path, ctx: Context, fusion_type="AVG_BLEND", block_scale=(
                 cur_h = nh
                 cur_size = [cur_size[d] // rel[d] for d in range(3)]
                 cur_off = [cur_off[d] // rel[d] for d in range(3)]
-                gp = tuple(cur_off[d] // bs[d] for d in range(3))
                 blk = ctx.volume_download(cur_h, cur_size, np_dt)
-                if all(cur_off[d] % bs[d] == 0 for d in range(3)):
-                    store.save_block(lv["dataset"], blk, gp)
-                else:   # lower-level piece that does not start on a storage-block boundary: read-modify-write
-                    _write_region(store, lv["dataset"], blk, cur_off)
+                # a lower-level piece generally covers only part of a storage block (and may not start
+                # on a block boundary): read-modify-write of full-extent blocks
+                _write_region(store, lv["dataset"], blk, cur_off)
             ctx.volume_free(cur_h)
     for h in supplier.handles.values():
         ctx.volume_free(h)
