@@ -291,6 +291,18 @@ __global__ void fuse_plan_kernel(const FuseViewDev* __restrict__ views, int nvie
     p.overflow = overflow;
 }
 
+template <int OUT>
+__device__ __forceinline__ void store_voxel(const FuseArgs& a, size_t o, float res) {
+    if (OUT == BS_DTYPE_F32) {
+        __stcs((float*)a.out + o, res);
+    } else {
+        double c = floor(((double)res - a.cmin) * a.cscale + 0.5);
+        c = fmin(fmax(c, 0.0), a.ctop);
+        if (OUT == BS_DTYPE_U16) ((unsigned short*)a.out)[o] = (unsigned short)c;
+        else ((unsigned char*)a.out)[o] = (unsigned char)c;
+    }
+}
+
 // KIND 0: weighted average family (AVG, AVG_BLEND, *_CONTENT); KIND 1: winner family.
 // ACCUM: add partial sums into acc_wi/acc_w instead of producing the final voxel.
 //
@@ -347,6 +359,58 @@ fuse_kernel(const FuseViewDev* __restrict__ views, int nviews, FuseArgs a) {
             int* dst = reinterpret_cast<int*>(s_vt);
             for (int i = tid; i < nwords; i += NT) dst[i] = __ldg(src + i);
             __syncthreads();
+            if (KIND == 0 && !ACCUM && nact <= 1) {
+                // ---- fast path (the majority of tiles): zero or one view.  The weighted average of a
+                // single view is the sample itself wherever its weight is positive, so the voxels are
+                // written straight from the tap loop -- no accumulators, no epilogue.
+                const size_t plane = (size_t)a.size[1] * a.size[0];
+                size_t o = ((size_t)z0 * a.size[1] + y) * a.size[0] + x;
+                if (nact == 0) {
+                    if (valid)
+                        for (int k = 0; k < nz; ++k, o += plane) store_voxel<OUT>(a, o, 0.f);
+                    return;
+                }
+                const ViewTile& t = s_vt[0];
+                const bool staged = t.staged != 0;
+                if (staged) {
+                    stage_fixed_any(s_stage, t.data, t.dtype, t, tid);
+                    if (use_content) stage_fixed(s_stage_c, t.content, t, tid);
+                    __syncthreads();
+                }
+                if (!valid) return;
+                float rx = fmaf(t.m[0], tx, fmaf(t.m[1], ty, t.o[0]));
+                float ry = fmaf(t.m[3], tx, fmaf(t.m[4], ty, t.o[1]));
+                float rz = fmaf(t.m[6], tx, fmaf(t.m[7], ty, t.o[2]));
+                const float sxk = t.m[2], syk = t.m[5], szk = t.m[8];
+                const float bx = (float)t.b0[0], by = (float)t.b0[1], bz = (float)t.b0[2];
+                const float dm1x = (float)(t.dims[0] - 1), dm1y = (float)(t.dims[1] - 1), dm1z = (float)(t.dims[2] - 1);
+                const bool do_blend = use_blend && !t.plateau;
+                const int mode = staged ? (t.interior ? 0 : 1) : 2;
+#pragma unroll 1
+                for (int k = 0; k < nz; ++k, rx += sxk, ry += syk, rz += szk, o += plane) {
+                    const float fx = rx + bx, fy = ry + by, fz = rz + bz;
+                    float res = 0.f;
+                    if (fx >= 0.f && fx <= dm1x && fy >= 0.f && fy <= dm1y && fz >= 0.f && fz <= dm1z) {
+                        float w = 1.f;
+                        bool ok = true;
+                        if (do_blend)
+                            ok = blend_axis(fx, dm1x, t.border[0], t.inv_range[0], a.lut_n, s_lut, w) &&
+                                 blend_axis(fy, dm1y, t.border[1], t.inv_range[1], a.lut_n, s_lut, w) &&
+                                 blend_axis(fz, dm1z, t.border[2], t.inv_range[2], a.lut_n, s_lut, w);
+                        if (ok && use_content) {
+                            if (staged) w *= sample_staged<false>(s_stage_c, t, fmaxf(rx, 0.f), fmaxf(ry, 0.f), fmaxf(rz, 0.f));
+                            else w *= sample<float, LINEAR>(t.content, t.dims[0], t.dims[1], t.dims[2], fx, fy, fz);
+                        }
+                        if (ok && w > 0.f) {
+                            if (mode == 0) res = sample_staged<true>(s_stage, t, fmaxf(rx, 0.f), fmaxf(ry, 0.f), fmaxf(rz, 0.f));
+                            else if (mode == 1) res = sample_staged<false>(s_stage, t, fmaxf(rx, 0.f), fmaxf(ry, 0.f), fmaxf(rz, 0.f));
+                            else res = sample_any<LINEAR>(t.data, t.dtype, t.dims[0], t.dims[1], t.dims[2], fx, fy, fz);
+                        }
+                    }
+                    store_voxel<OUT>(a, o, res);
+                }
+                return;
+            }
         } else {
             __syncthreads();
             if (tid == 0) s_nactive = 0;
