@@ -137,3 +137,11 @@ def test_large_single_axis_generic_path(ctx):
     a, b = synth.shifted_pair((12, 20, 780), (9, -2, 1), seed=70, margin=12)
     g, o = _check(ctx, a, b)           # GPU == oracle (bit-identical shift, 1e-3 sub-pixel)
     assert g.shift_int[:2] == (9, -2)  # 12 z-slices carry too little signal to pin the z component
+
+
+def test_long_aligned_rows_cta_tma_path(ctx):
+    """x pad 810 (M = 405 > 319) with 16-byte-multiple rows (784 * 2 B): the CTA-level TMA-staged
+    r2c kernel with a runtime-planned FFT."""
+    a, b = synth.shifted_pair((10, 24, 784), (-6, 3, 0), seed=71, margin=12)
+    g, o = _check(ctx, a, b)
+    assert g.pad[0] == 810 and g.shift_int[:2] == (-6, 3)
