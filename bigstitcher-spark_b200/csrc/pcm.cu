@@ -1798,11 +1798,18 @@ int bs_pcm_batch(bs_ctx* ctx, int n, const void* const* img1, const void* const*
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (n < 0 || (n > 0 && (!img1 || !img2 || !dims || !params || !out)))
         return bs_set_error(ctx, BS_ERR_ARG, "bs_pcm_batch: NULL argument");
+    if (n == 0) return BS_OK;
     BS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n > 0 && (params->peaks_to_check < 1 || params->peaks_to_check > PCM_KMAX))
+        return bs_set_error(ctx, BS_ERR_ARG, "pcm: peaks_to_check must be in [1,%d]", PCM_KMAX);
     for (int i = 0; i < n; ++i) {
         if (!img1[i] || !img2[i]) return bs_set_error(ctx, BS_ERR_ARG, "bs_pcm_batch: pair %d has a NULL image", i);
         for (int d = 0; d < 3; ++d)
             if (dims[3 * i + d] <= 0) return bs_set_error(ctx, BS_ERR_ARG, "bs_pcm_batch: pair %d has dims[%d] <= 0", i, d);
+        // validate every pair's geometry BEFORE any byte is copied or any kernel is launched
+        PcmGeometry g;
+        const int rc = pcm_geometry(ctx, dims + 3 * i, params->extension, &g);
+        if (rc) return rc;
     }
     if (on_device) {
         for (int i = 0; i < n; ++i) {

@@ -145,3 +145,13 @@ def test_long_aligned_rows_cta_tma_path(ctx):
     a, b = synth.shifted_pair((10, 24, 784), (-6, 3, 0), seed=71, margin=12)
     g, o = _check(ctx, a, b)
     assert g.pad[0] == 810 and g.shift_int[:2] == (-6, 3)
+
+
+def test_oversized_dims_rejected_before_any_copy(ctx):
+    """Maximum sizes: an axis beyond 16384 is refused up front (nothing is read from the host buffers)."""
+    import bsgpu
+    a = np.zeros((8, 8, 8), np.uint16)
+    with pytest.raises(bsgpu.BsError) as e:
+        ctx.pcm_pair(a, a, dims_xyz=(20000, 8, 8))
+    assert "out of range" in str(e.value)
+    assert ctx.pcm_batch([], []) == []          # empty batch is a no-op
