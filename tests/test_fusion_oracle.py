@@ -136,3 +136,21 @@ def test_downsample_known_answers():
     assert fo.downsample2x(v, (2, 2, 2)).shape == (1, 1, 2) and fo.downsample2x(v, (2, 2, 2))[0, 0, 0] == 6.5
     u = np.array([[[1, 2, 3, 4, 9]]], dtype=np.uint16)
     assert list(fo.downsample2x(u, (2, 1, 1)).ravel()) == [2, 4]    # (1+2+1)>>1, (3+4+1)>>1, odd tail dropped
+
+
+def test_c_restatement_matches_numpy_oracle():
+    """oracle/c/fusion_oracle.c (the CPU-baseline arm) against the numpy oracle on a jittered 3-view scene."""
+    from oracle import c_fusion
+    G = synth.field((30, 44, 120), seed=4, sigma=1.5)
+    views = []
+    for i, t in enumerate([(0.3, 0.1, -0.2), (31.7, 1.4, 2.1), (64.2, -2.2, 0.6)]):
+        vol = synth.tile_from(G, (2, 3, int(t[0]) + 4), (24, 36, 44), 20 + i, noise=5.0)
+        M = synth.translation(t)
+        border, rng = fo.adjust_blending(M)
+        views.append(fo.View(vol, M, border, rng))
+    for ft in (fo.AVG, fo.AVG_BLEND):
+        want = fo.fuse_block(views, (-2, -1, -1), (112, 40, 28), ft)
+        got = c_fusion.fuse_block(views, (-2, -1, -1), (112, 40, 28), ft)
+        assert np.allclose(got, want, rtol=2e-6, atol=1e-4)
+        assert np.array_equal(got == 0, want == 0)
+    assert c_fusion.num_threads() >= 1
