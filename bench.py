@@ -207,8 +207,10 @@ def cpu_fusion_sample(procs, blocks_per_proc=2, tile=160, bs=96):
 
 
 def cpu_layout():
+    """All host threads: ncores/4 concurrent single-pair workers (capped at 32: ~6 GB each) x 4 FFT
+    threads -- the shape of the reference's Spark local[N] (one task per slot)."""
     ncores = os.cpu_count() or 1
-    procs = max(1, min(16, ncores // 4))
+    procs = max(1, min(32, ncores // 4))
     threads = max(1, min(4, ncores // procs))
     return ncores, procs, threads
 
