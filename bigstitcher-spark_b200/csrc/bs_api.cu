@@ -103,9 +103,12 @@ void bs_destroy(bs_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
     bs_profile_drain(ctx);
-    for (auto& kv : ctx->vols)
+    for (auto& kv : ctx->vols) {
         if (kv.second.owned && kv.second.dev) cudaFree(kv.second.dev);
+        if (kv.second.tmaps_dev) cudaFree(kv.second.tmaps_dev);
+    }
     bs_pcm_workspace_free(ctx);
+    bs_fuse2_free(ctx);
     if (ctx->fuse_ring_dev) cudaFree(ctx->fuse_ring_dev);
     if (ctx->fuse_ring_host) cudaFreeHost(ctx->fuse_ring_host);
     for (int i = 0; i < bs_ctx::kFuseSlots; ++i)
@@ -229,10 +232,11 @@ int bs_volume_free(bs_ctx* ctx, unsigned long long handle) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     auto it = ctx->vols.find(handle);
     if (it == ctx->vols.end()) return bs_set_error(ctx, BS_ERR_ARG, "bs_volume_free: unknown handle %llu", handle);
-    if (it->second.owned) {
+    if (it->second.owned || it->second.tmaps_dev) {
         BS_CUDA(ctx, cudaSetDevice(ctx->device));
         BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        BS_CUDA(ctx, cudaFree(it->second.dev));
+        if (it->second.owned) BS_CUDA(ctx, cudaFree(it->second.dev));
+        if (it->second.tmaps_dev) BS_CUDA(ctx, cudaFree(it->second.tmaps_dev));
     }
     ctx->vols.erase(it);
     return BS_OK;

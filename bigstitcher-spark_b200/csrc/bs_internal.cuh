@@ -16,6 +16,8 @@ struct bs_volume {
     long long dims[3] = {0, 0, 0};
     int dtype = 0;
     bool owned = false;
+    void* tmaps_dev = nullptr;   // device copies of the volume's TMA tensor maps (fuse_tma.cu), lazily built
+    int tma_state = 0;           // 0 not tried, 1 available, -1 not eligible (dtype / alignment / pitch)
 };
 
 struct bs_prof_entry {
@@ -70,6 +72,7 @@ struct bs_ctx {
     size_t fuse_plan_cap = 0;
     void* fuse_out = nullptr;         // device staging for host outputs
     size_t fuse_out_cap = 0;
+    void* fuse2 = nullptr;            // fuse_tma.cu workspace (Fuse2Ws)
     int sm_count = 148;
     bool pcm_attr_done = false;       // cudaFuncSetAttribute(max dynamic smem) done on this device
 };
@@ -114,3 +117,9 @@ int bs_ensure_dev(bs_ctx* ctx, void** p, size_t* cap, size_t need);
 
 // pcm.cu
 void bs_pcm_workspace_free(bs_ctx* ctx);
+// fuse_tma.cu
+void bs_fuse2_free(bs_ctx* ctx);
+// fuse.cu: generic tile kernel for one block into a device buffer (ctx->mu held by the caller)
+int bs_fuse_legacy_block(bs_ctx* ctx, const bs_view* views, int n_views, const long long block_min[3],
+                         const long long block_size[3], const bs_fuse_params* params, void* out_dev);
+int bs_fuse_validate(bs_ctx* ctx, const bs_view* views, int n_views, const bs_fuse_params* p);

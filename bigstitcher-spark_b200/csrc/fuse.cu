@@ -12,12 +12,12 @@
 #include <cstring>
 
 #include "bs_internal.cuh"
+#include "fuse_common.cuh"
 
 #define FUSE_TX 32
 #define FUSE_TY 8
 #define FUSE_ZT 8
 #define FUSE_CHUNK 32
-#define FUSE_MAX_LUT 256
 
 struct FuseViewDev {
     double inv[12];        // world -> source pixel
@@ -179,37 +179,6 @@ __device__ __forceinline__ float sample_staged(const float* __restrict__ st, con
     const float c0 = c00 + ty * (c01 - c00);
     const float c1 = c10 + ty * (c11 - c10);
     return c0 + tz * (c1 - c0);
-}
-
-// cosine blending weight along one axis (l = absolute source coordinate); false when weight is 0
-__device__ __forceinline__ bool blend_axis(float l, float dm1, float border, float inv_range, int lut_n,
-                                           const float* s_lut, float& w) {
-    const float dist = fmaxf(0.f, fminf(l - border, (dm1 - l) - border));
-    if (dist == 0.f) return false;
-    const float rel = dist * inv_range;
-    if (rel < 1.f) {
-        float f;
-        if (lut_n > 0) {
-            const float pos = rel * (float)lut_n;
-            const int i = (int)pos;
-            const float s = pos - (float)i;
-            f = s_lut[i] * (1.0f - s) + s_lut[i + 1] * s;
-        } else {
-            // (cos((1 - rel) pi) + 1) / 2 == sin^2(pi rel / 2): no cancellation for tiny weights.
-            // sin(pi y), y = rel / 2 in [0, 0.5): odd Taylor polynomial to y^11 (rel. error < 1e-7)
-            const float yh = 0.5f * rel, y2 = yh * yh;
-            float p = -0.0073704309f;              // -pi^11 / 11!
-            p = fmaf(p, y2, 0.0821458866f);         //  pi^9 / 9!
-            p = fmaf(p, y2, -0.5992645293f);        // -pi^7 / 7!
-            p = fmaf(p, y2, 2.5501640399f);         //  pi^5 / 5!
-            p = fmaf(p, y2, -5.1677127800f);        // -pi^3 / 3!
-            p = fmaf(p, y2, 3.1415926536f);         //  pi
-            const float sn = p * yh;
-            f = sn * sn;
-        }
-        w *= f;
-    }
-    return true;
 }
 
 // Cull one view against one output tile and derive its tile constants (double precision once per
@@ -544,24 +513,25 @@ __global__ void fuse_finish_kernel(const float* __restrict__ swi, const float* _
 }
 
 // ------------------------------------------------------------------------------------------
-static bool invert34(const double* m, double* inv) {
-    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
-    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
-    if (det == 0.0 || !std::isfinite(det)) return false;
-    const double id = 1.0 / det;
-    double A[9] = {(e * i - f * h) * id, (c * h - b * i) * id, (b * f - c * e) * id,
-                   (f * g - d * i) * id, (a * i - c * g) * id, (c * d - a * f) * id,
-                   (d * h - e * g) * id, (b * g - a * h) * id, (a * e - b * d) * id};
-    for (int r = 0; r < 3; ++r) {
-        inv[4 * r + 0] = A[3 * r + 0];
-        inv[4 * r + 1] = A[3 * r + 1];
-        inv[4 * r + 2] = A[3 * r + 2];
-        inv[4 * r + 3] = -(A[3 * r + 0] * m[3] + A[3 * r + 1] * m[7] + A[3 * r + 2] * m[11]);
-    }
-    return true;
+int bs_fuse_validate(bs_ctx* ctx, const bs_view* views, int n_views, const bs_fuse_params* p) {
+    if (!views && n_views > 0) return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: views is NULL");
+    if (!p) return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: NULL argument");
+    if (n_views < 0) return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: n_views < 0");
+    if (p->fusion_type < BS_FUSE_AVG || p->fusion_type > BS_FUSE_CLOSEST_PIXEL_WINS)
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: unknown fusion_type %d", p->fusion_type);
+    if (p->interpolation != 0 && p->interpolation != 1)
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: interpolation must be 0 or 1");
+    if (p->out_dtype != BS_DTYPE_F32 && p->out_dtype != BS_DTYPE_U16 && p->out_dtype != BS_DTYPE_U8)
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: bad out_dtype %d", p->out_dtype);
+    if (p->blend_lut_n < 0 || p->blend_lut_n > FUSE_MAX_LUT)
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: blend_lut_n out of range [0,%d]", FUSE_MAX_LUT);
+    if (p->out_dtype != BS_DTYPE_F32 && !(p->max_intensity > p->min_intensity))
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: max_intensity must exceed min_intensity");
+    for (int i = 0; i < n_views; ++i)
+        if (ctx->vols.find(views[i].vol_handle) == ctx->vols.end())
+            return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: view %d has unknown vol_handle %llu", i, views[i].vol_handle);
+    return BS_OK;
 }
-
-static size_t out_elem_size(int dt) { return dt == BS_DTYPE_F32 ? 4 : dt == BS_DTYPE_U16 ? 2 : 1; }
 
 struct FusePrepared {
     FuseArgs args;
@@ -598,7 +568,7 @@ static int fuse_prepare(bs_ctx* ctx, const bs_view* views, int n_views, const lo
             return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: view %d has unknown vol_handle %llu", i, views[i].vol_handle);
         const bs_volume& vol = it->second;
         FuseViewDev& d = hv[i];
-        if (!invert34(views[i].src_to_world, d.inv))
+        if (!bs_invert34(views[i].src_to_world, d.inv))
             return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: view %d has a singular transform", i);
         d.data = vol.dev;
         d.dims[0] = (int)vol.dims[0]; d.dims[1] = (int)vol.dims[1]; d.dims[2] = (int)vol.dims[2];
@@ -736,64 +706,19 @@ void bs_fuse_default_params(bs_fuse_params* p) {
     p->max_intensity = 65535.0;
 }
 
-int bs_fuse_block(bs_ctx* ctx, const bs_view* views, int n_views, const long long block_min[3],
-                  const long long block_size[3], const bs_fuse_params* params, void* out, int out_on_device) {
-    if (!ctx) return BS_ERR_ARG;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    if (!out) return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse_block: out is NULL");
-    BS_CUDA(ctx, cudaSetDevice(ctx->device));
+}  // extern "C"
+
+// generic tile kernel for one block into a device buffer; the caller holds ctx->mu
+int bs_fuse_legacy_block(bs_ctx* ctx, const bs_view* views, int n_views, const long long block_min[3],
+                         const long long block_size[3], const bs_fuse_params* params, void* out_dev) {
     FusePrepared prep;
     int rc = fuse_prepare(ctx, views, n_views, block_min, block_size, params, &prep);
     if (rc) return rc;
-    const size_t bytes = (size_t)block_size[0] * block_size[1] * block_size[2] * out_elem_size(params->out_dtype);
-    if (out_on_device) {
-        prep.args.out = out;
-    } else {
-        rc = bs_ensure_dev(ctx, &ctx->fuse_out, &ctx->fuse_out_cap, bytes);
-        if (rc) return rc;
-        prep.args.out = ctx->fuse_out;
-    }
-    rc = fuse_launch(ctx, prep, params, false);
-    if (rc) return rc;
-    if (!out_on_device) {
-        BS_CUDA(ctx, cudaMemcpyAsync(out, ctx->fuse_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
-    return BS_OK;
+    prep.args.out = out_dev;
+    return fuse_launch(ctx, prep, params, false);
 }
 
-int bs_fuse_block_to_volume(bs_ctx* ctx, const bs_view* views, int n_views, const long long block_min[3],
-                            const long long block_size[3], const bs_fuse_params* params, unsigned long long* out_handle) {
-    if (!ctx) return BS_ERR_ARG;
-    if (!out_handle || !block_size || !params) return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse_block_to_volume: NULL argument");
-    void* dev = nullptr;
-    {
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        for (int d = 0; d < 3; ++d)
-            if (block_size[d] <= 0 || block_size[d] > 0x7fffffffLL)
-                return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse_block_to_volume: bad block_size");
-        BS_CUDA(ctx, cudaSetDevice(ctx->device));
-        BS_CUDA(ctx, cudaMalloc(&dev, (size_t)block_size[0] * block_size[1] * block_size[2] * out_elem_size(params->out_dtype)));
-    }
-    int rc = bs_fuse_block(ctx, views, n_views, block_min, block_size, params, dev, 1);
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    if (rc == BS_OK) {
-        cudaError_t e = cudaStreamSynchronize(ctx->stream);
-        if (e != cudaSuccess) rc = bs_set_error(ctx, BS_ERR_CUDA, "bs_fuse_block_to_volume: %s", cudaGetErrorString(e));
-    }
-    if (rc != BS_OK) {
-        cudaFree(dev);
-        return rc;
-    }
-    bs_volume v;
-    v.dev = dev;
-    v.dims[0] = block_size[0]; v.dims[1] = block_size[1]; v.dims[2] = block_size[2];
-    v.dtype = params->out_dtype;
-    v.owned = true;
-    *out_handle = ctx->next_handle++;
-    ctx->vols[*out_handle] = v;
-    return BS_OK;
-}
+extern "C" {
 
 int bs_fuse_accumulate(bs_ctx* ctx, const bs_view* views, int n_views, const long long block_min[3],
                        const long long block_size[3], const bs_fuse_params* params, float* sum_wi_dev,
@@ -825,7 +750,7 @@ int bs_fuse_finish(bs_ctx* ctx, const float* sum_wi_dev, const float* sum_w_dev,
     a.ctop = params->out_dtype == BS_DTYPE_U8 ? 255.0 : 65535.0;
     a.cmin = params->min_intensity;
     a.cscale = params->out_dtype == BS_DTYPE_F32 ? 1.0 : a.ctop / (params->max_intensity - params->min_intensity);
-    const size_t bytes = (size_t)n * out_elem_size(params->out_dtype);
+    const size_t bytes = (size_t)n * bs_out_elem_size(params->out_dtype);
     if (out_on_device) {
         a.out = out;
     } else {

@@ -81,7 +81,8 @@ SYMBOLS = [
     "bs_profile_enable", "bs_profile_reset", "bs_profile_get", "bs_host_alloc", "bs_host_free",
     "bs_pcm_default_params", "bs_pcm_pair", "bs_pcm_batch", "bs_good_fft_size", "bs_pcm_debug_pcm",
     "bs_fuse_default_params", "bs_volume_upload", "bs_volume_wrap", "bs_volume_free",
-    "bs_content_weights", "bs_volume_download", "bs_volume_devptr", "bs_downsample", "bs_fuse_block", "bs_fuse_block_to_volume", "bs_fuse_accumulate", "bs_fuse_finish",
+    "bs_content_weights", "bs_volume_download", "bs_volume_devptr", "bs_downsample", "bs_fuse_block", "bs_fuse_blocks",
+    "bs_fuse_block_to_volume", "bs_fuse_accumulate", "bs_fuse_finish",
 ]
 
 
@@ -127,6 +128,7 @@ def load_library():
     lib.bs_volume_devptr.argtypes = [vp, ull, P(vp)]
     lib.bs_downsample.argtypes = [vp, ull, P(ip), P(ull)]
     lib.bs_fuse_block.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), vp, ip]
+    lib.bs_fuse_blocks.argtypes = [vp, P(ViewC), ip, ip, P(ll), P(ll), P(FuseParamsC), P(vp), ip]
     lib.bs_fuse_block_to_volume.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), P(ull)]
     lib.bs_fuse_accumulate.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), vp, vp]
     lib.bs_fuse_finish.argtypes = [vp, vp, vp, ll, P(FuseParamsC), vp, ip]
@@ -359,6 +361,32 @@ class Context:
         p, on_dev, _ = _ptr_of(out)
         self._check(self.lib.bs_fuse_block(self.h, arr, n, bmin, bsz, C.byref(params), p, 1 if on_dev else 0))
         return out
+
+    def fuse_blocks(self, views, block_mins_xyz, block_sizes_xyz, params: FuseParamsC | None = None, outs=None):
+        """Fuse a list of blocks in one call (one plan pass + one launch).  ``outs``: list of numpy arrays or
+        device tensors / pointers (all on the same side); allocated as numpy arrays when None."""
+        params = params or self.fuse_params()
+        arr, n = views if isinstance(views, tuple) else self.make_views(views)
+        nb = len(block_mins_xyz)
+        bmin = (C.c_longlong * (3 * max(nb, 1)))()
+        bsz = (C.c_longlong * (3 * max(nb, 1)))()
+        for i in range(nb):
+            bmin[3 * i:3 * i + 3] = [int(v) for v in block_mins_xyz[i]]
+            bsz[3 * i:3 * i + 3] = [int(v) for v in block_sizes_xyz[i]]
+        if outs is None:
+            outs = [np.empty(tuple(int(v) for v in s)[::-1], dtype=_BS2NP[params.out_dtype]) for s in block_sizes_xyz]
+        ptrs = (C.c_void_p * max(nb, 1))()
+        on_dev = None
+        keep = []
+        for i, o in enumerate(outs):
+            p, d, k = _ptr_of(o)
+            if on_dev is not None and d != on_dev:
+                raise ValueError("all outputs must live on the same side (host or device)")
+            on_dev = d
+            ptrs[i] = p
+            keep.append(k)
+        self._check(self.lib.bs_fuse_blocks(self.h, arr, n, nb, bmin, bsz, C.byref(params), ptrs, 1 if on_dev else 0))
+        return outs
 
     def fuse_block_to_volume(self, views, block_min_xyz, block_size_xyz, params: FuseParamsC | None = None) -> int:
         """Fuse one block into a new resident volume; returns its handle."""

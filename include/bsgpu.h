@@ -171,6 +171,14 @@ int bs_fuse_block(bs_ctx* ctx, const bs_view* views, int n_views, const long lon
                   const long long block_size[3], const bs_fuse_params* params,
                   void* out, int out_on_device);
 
+/* the same for a LIST of blocks in one call (one plan pass, one kernel launch for the whole list; host
+ * destinations are staged through two device buffers so the D2H copies of one group of blocks overlap the
+ * fusion of the next).  block_min / block_size: n_blocks x 3; outs: n_blocks destination pointers, each a
+ * dense x-fastest block like bs_fuse_block's.  This is the work-queue form of the reference's
+ * rdd.map(gridBlock -> fuse + save) (J/SparkAffineFusion.java:480-482, 602-670). */
+int bs_fuse_blocks(bs_ctx* ctx, const bs_view* views, int n_views, int n_blocks, const long long* block_min,
+                   const long long* block_size, const bs_fuse_params* params, void* const* outs, int out_on_device);
+
 /* same, but the fused block stays on the device as a new resident volume (handle): the pyramid
  * levels are then derived with bs_downsample before anything is downloaded (next row 8f-3) */
 int bs_fuse_block_to_volume(bs_ctx* ctx, const bs_view* views, int n_views, const long long block_min[3],

@@ -42,3 +42,22 @@ def rot_z(deg, center_xyz=(0, 0, 0)):
 def translation(t_xyz):
     M = np.hstack([np.eye(3), np.asarray(t_xyz, dtype=np.float64)[:, None]])
     return M
+
+
+def subpixel_pair(shape_zyx, shift_xyz, seed=0, margin=24, sigma=1.5, noise=20.0, dtype=np.uint16, workers=-1):
+    """img2(p) = img1(p + shift) with a REAL-valued shift: the common field is translated in the
+    Fourier domain ("additional Fourier-domain sub-pixel shift"), then both tiles are
+    cropped at the same offset."""
+    from scipy import fft as sfft
+    big = tuple(s + 2 * margin for s in shape_zyx)
+    G = field(big, seed=seed, sigma=sigma)
+    F = sfft.rfftn(G, workers=workers)
+    sx, sy, sz = shift_xyz
+    kz = sfft.fftfreq(big[0])[:, None, None]
+    ky = sfft.fftfreq(big[1])[None, :, None]
+    kx = sfft.rfftfreq(big[2])[None, None, :]
+    F *= np.exp(2j * np.pi * (kz * sz + ky * sy + kx * sx)).astype(np.complex64)  # G2(p) = G(p + s)
+    G2 = sfft.irfftn(F, s=big, workers=workers).astype(np.float32)
+    a = tile_from(G, (margin,) * 3, shape_zyx, 1000 + seed, noise, dtype)
+    b = tile_from(G2, (margin,) * 3, shape_zyx, 2000 + seed, noise, dtype)
+    return a, b

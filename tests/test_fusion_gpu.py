@@ -80,7 +80,12 @@ def _assert_close(got, want, rtol=RTOL):
         bad = np.argwhere(err > rtol)
         assert len(bad) <= 1e-3 * got.size + 2, f"{len(bad)} voxels beyond rtol, max {err.max()}"
         for idx in bad:
-            assert _near_view_face(tuple(idx)), f"rel err {err[tuple(idx)]} at {tuple(idx)} away from any view face"
+            # (a) on a face the inside / dist == 0 tests may flip; (b) within ~1.5 px of a face of EVERY
+            # contributing view the blending weights are 1e-6..1e-3 and sum(w I) / sum(w) amplifies the
+            # 3e-5 px float rounding of the source coordinate (2 dw/w = 2 * 3e-5 / dist): bounded at 3e-3 there
+            e = err[tuple(idx)]
+            assert _near_view_face(tuple(idx)) or (e < 3e-3 and _near_view_face(tuple(idx), tol=1.5)), \
+                f"rel err {e} at {tuple(idx)} away from any view face"
     else:
         d = np.abs(got.astype(np.int64) - want.astype(np.int64))
         # one grey level at most, and only where the float result sits within ~1e-7 rel of a rounding
@@ -251,3 +256,69 @@ def test_device_pyramid_step_bit_exact(ctx, dtype, factors):
     assert np.array_equal(got, want)
     ctx.volume_free(h)
     ctx.volume_free(h2)
+
+
+# ---- the code paths bench.py runs (BASELINE configs[2]): big tiles, so that whole output tiles lie on the
+# blending plateau / strictly inside one view (single-view fast path), next to multi-view blend zones.
+def _run_c(ctx, views, bmin, bsize, fusion_type=fo.AVG_BLEND):
+    """GPU block vs the C/OpenMP oracle (oracle/c_fusion, itself checked against the numpy oracle)."""
+    from oracle import c_fusion
+    handles = [ctx.volume_upload(v) for v, _ in views]
+    ov, gv = [], []
+    for (vol, M), h in zip(views, handles):
+        border, rng = fo.adjust_blending(M)
+        ov.append(fo.View(vol, M, border, rng, None))
+        gv.append(dict(src_to_world=M, vol_handle=h, blend_border=border, blend_range=rng))
+    got = ctx.fuse_block(gv, bmin, bsize, ctx.fuse_params(fusion_type))
+    want = c_fusion.fuse_block(ov, bmin, bsize, fusion_type)
+    for h in handles:
+        ctx.volume_free(h)
+    _run.last = (ov, bmin, bsize)
+    return got, want
+
+
+def _sparse_tile(shape_zyx, region_zyx, seed):
+    """uint16 tile that is zero except for a smooth random sub-region (keeps 576^3 tiles cheap)."""
+    from scipy.ndimage import gaussian_filter
+    vol = np.zeros(shape_zyx, np.uint16)
+    sl = tuple(slice(max(0, a), min(s, b)) for (a, b), s in zip(region_zyx, shape_zyx))
+    shp = tuple(s.stop - s.start for s in sl)
+    rng = np.random.default_rng(seed)
+    g = gaussian_filter(rng.standard_normal(shp).astype(np.float32), 1.5)
+    vol[sl] = np.clip(np.rint(g / g.std() * 300 + 1000), 0, 65535).astype(np.uint16)
+    return vol
+
+
+@pytest.mark.parametrize("rot", [0.0, 0.5])
+def test_large_tiles_all_fast_paths(ctx, rot):
+    shape = (160, 168, 176)
+    views = _scene(seed=21, n=2, shape=shape, rot=rot)
+    got, want = _run_c(ctx, views, (-4, -3, -2), (344, 180, 168))
+    _assert_close(got, want)
+    assert np.count_nonzero(want) > 0.7 * want.size
+
+
+@pytest.mark.parametrize("rot", [0.0, 0.5])
+def test_config3_superblock_576_tiles(ctx, rot):
+    """One real BASELINE configs[2] task: a 256x256x128 super-block at the junction of eight 576^3 tiles
+    (stride 491, jitter in [-2,2]^3), float32 AVG_BLEND, against the C oracle at 1e-4."""
+    tile, stride = 576, 491
+    bmin, bsize = (384, 384, 448), (256, 256, 128)
+    rng = np.random.default_rng(7)
+    a = np.deg2rad(rot)
+    R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+    views = []
+    for k in range(2):
+        for j in range(2):
+            for i in range(2):
+                t = stride * np.array([i, j, k], dtype=np.float64) + rng.uniform(-2, 2, 3)
+                c = np.array([tile / 2, tile / 2, 0.0])
+                M = np.hstack([R, (t + c - R @ c)[:, None]])
+                # source region the block can touch (+ margin), in this tile's pixel coordinates
+                lo = np.array(bmin) - t - 12
+                hi = np.array(bmin) + np.array(bsize) - t + 12
+                region = [(int(lo[d]), int(hi[d])) for d in (2, 1, 0)]
+                views.append((_sparse_tile((tile,) * 3, region, 100 + 4 * k + 2 * j + i), M))
+    got, want = _run_c(ctx, views, bmin, bsize)
+    _assert_close(got, want)
+    assert np.count_nonzero(want) > 0.9 * want.size

@@ -155,3 +155,47 @@ def test_oversized_dims_rejected_before_any_copy(ctx):
         ctx.pcm_pair(a, a, dims_xyz=(20000, 8, 8))
     assert "out of range" in str(e.value)
     assert ctx.pcm_batch([], []) == []          # empty batch is a no-op
+
+
+# ---- the code paths bench.py runs: compile-time plans for padded length 540 (x: FftWStatic<270>, y/z:
+# FftStatic<540> two-stage 27x20, cp.async pipelined y pass, z cross-power pass).  The static plans are
+# selected per axis, so three thin crops reach each of them cheaply; the full 512^3 pair is the bench unit.
+@pytest.mark.parametrize("shape,shift", [
+    ((24, 24, 500), (7, -3, 2)),     # x pads to 540  -> k_fft_x_r2c_w / k_fft_x_c2r_w <FftWStatic<270>>
+    ((24, 500, 24), (-2, 9, 1)),     # y pads to 540  -> k_fft_strided_pipe <FftStatic<540>>
+    ((500, 24, 24), (3, 2, -11)),    # z pads to 540  -> k_fft_strided mode 1 (cross-power) <FftStatic<540>>
+    ((500, 500, 24), (1, -8, 6)),    # y and z static, x generic
+])
+def test_static_540_plans_thin_crops(ctx, shape, shift):
+    a, b = synth.shifted_pair(shape, shift, seed=80 + shape[0] % 7, margin=16)
+    g, o = _check(ctx, a, b)
+    assert 540 in g.pad
+    pg = ctx.pcm_debug_pcm(a, b)
+    pc = po.calculate_pcm(a, b, workers=-1)
+    assert np.abs(pg - pc).max() < 2e-4 * np.abs(pc).max()
+
+
+def test_static_540_thin_subpixel(ctx):
+    a, b = synth.subpixel_pair((24, 500, 500), (4.3, -6.25, 1.4), seed=85, margin=16)
+    g, o = _check(ctx, a, b)
+    assert g.pad[0] == 540 and g.pad[1] == 540
+    assert g.shift_int[:2] == (4, -6)
+    assert abs(g.shift_sub[0] - 4.3) < 0.15 and abs(g.shift_sub[1] + 6.25) < 0.15   # known answer (fit bias)
+
+
+def test_full_512_pair_subpixel_bench_unit(ctx):
+    """One full BASELINE configs[1] unit: 512^3 uint16 pair with a planted SUB-PIXEL shift, all three axes
+    on the static 540 plans -- every kernel bench.py times, against the oracle (sub 1e-3, r 1e-9, index
+    bit-identical, PCM volume 2e-4)."""
+    a, b = synth.subpixel_pair((512, 512, 512), (11.37, -4.62, 7.3), seed=90, margin=20)
+    o = po.pcm_shift(a, b, workers=-1)
+    g = ctx.pcm_pair(a, b)
+    assert g.pad == o.pad == (540, 540, 540)
+    assert g.found and o.found
+    assert g.shift_int == o.shift_int and g.peak_index == o.peak_index
+    assert g.n_overlap_px == o.n_overlap_px and abs(g.r - o.r) < 1e-9
+    assert np.allclose(g.shift_sub, o.shift_sub, atol=1e-3), (g.shift_sub, o.shift_sub)
+    assert np.allclose(g.shift_sub, (11.37, -4.62, 7.3), atol=0.2)
+    pg = ctx.pcm_debug_pcm(a, b)
+    pc = po.calculate_pcm(a, b, workers=-1)
+    assert np.abs(pg - pc).max() < 2e-4 * np.abs(pc).max()
