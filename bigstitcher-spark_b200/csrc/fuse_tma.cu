@@ -39,11 +39,14 @@ constexpr int NTEAM = 256;                 // consumer threads per team (8 warps
 constexpr int NTEAMS = 2;                  // two teams work on alternate tiles of the CTA's run
 constexpr int NCONS = NTEAM * NTEAMS;
 constexpr int NTHREADS = NCONS + 32;       // + 1 producer warp
-constexpr int BXT = 72, BYT = 17, BZT = 9;     // translation box (uint16 elements; 65 x 17 x 9 needed)
-constexpr int BXG = 72, BYG = 20, BZG = 12;    // general box
+// TMA (tiled, no swizzle): the box start along the innermost dimension must be 16-byte aligned, i.e. a multiple
+// of 8 uint16 (an unaligned x coordinate raises "illegal instruction"); negative / out-of-range coordinates are
+// fine and zero-filled.  Boxes therefore start at floor8(x0) and carry up to 7 extra columns.
+constexpr int BXT = 72, BYT = 17, BZT = 9;     // translation box (uint16 elements; (7 +) 65 x 17 x 9 needed)
+constexpr int BXG = 80, BYG = 20, BZG = 12;    // general box (x origin is rounded down to a multiple of 8)
 constexpr int SLOT_T = ((BXT * BYT * BZT * 2 + 127) / 128) * 128;   // 22144 B
 constexpr int SLOT_G = ((BXG * BYG * BZG * 2 + 127) / 128) * 128;   // 34560 B
-constexpr int NST_T = 8, NST_G = 6;        // box slots per CTA (1 CTA per SM)
+constexpr int NST_T = 8, NST_G = 5;        // box slots per CTA (1 CTA per SM)
 constexpr int NTR = 4;                     // tile-record ring
 
 enum { VI_PLAT_X = 1, VI_PLAT_Y = 2, VI_PLAT_Z = 4, VI_INSIDE = 8, VI_FITS = 16 };
@@ -103,6 +106,8 @@ struct FuseArgs2 {
     const WorkRec* work;
     const TileHdr* hdr;
     const ViewItem* pool;
+    int* work_ctr;                // dynamic work distribution (zeroed per launch)
+    int nwork;
     int use_blend;
     double cmin, cscale, ctop;
 };
@@ -169,7 +174,8 @@ __device__ __forceinline__ CullOut cull_view(const ViewDev& v, int vi, const dou
             lo = org + fmin(0.0, m0 * ext[0]) + fmin(0.0, m1 * ext[1]) + fmin(0.0, m2 * ext[2]);
             hi = org + fmax(0.0, m0 * ext[0]) + fmax(0.0, m1 * ext[1]) + fmax(0.0, m2 * ext[2]);
             const double eps = 2e-3 + 2e-7 * fmax(fabs(lo), fabs(hi));
-            const int f0 = max((int)floor(fmax(lo - eps, 0.0)), 0);
+            int f0 = max((int)floor(fmax(lo - eps, 0.0)), 0);
+            if (a == 0) f0 &= ~7;                      // 16-byte aligned TMA box origin
             const int f1 = min((int)floor(fmin(hi + eps, dm1)), dim - 1) + 1;
             const int cap = a == 0 ? BXG : (a == 1 ? BYG : BZG);
             if (f1 - f0 + 1 > cap) r.fits = false;
@@ -294,15 +300,23 @@ __device__ __forceinline__ void store_pair(const FuseArgs2& a, typename OutT<OUT
 }
 
 // ------------------------------------------------------------------------------------------ translation tile
-// one z plane of the staged box -> the thread's 2 x 2 x/y-interpolated values (x then y, a + f (b - a))
-__device__ __forceinline__ void tr_plane(const unsigned int* __restrict__ rowbase, float fx, float fy, float (&c)[4]) {
+// one z plane of the staged box -> the thread's 2 x 2 x/y-interpolated values (x then y, a + f (b - a)).
+// uint16 -> float without the conversion pipe: PRMT builds 0x4B00hhll = 2^23 + v, differences of two such
+// floats are exact, and v itself is one FADD away.  sel01 packs taps (x0, x0+1) out of the two words the row
+// loads (x0 even: w0; x0 odd: w0.hi, w1.lo), sel2 picks tap x0+2 from w1.
+__device__ __forceinline__ void tr_plane(const unsigned int* __restrict__ rowbase, unsigned int sel01, unsigned int sel2,
+                                         float fx, float fy, float (&c)[4]) {
+    constexpr unsigned int MAG = 0x4B000000u;
     float r[3][2];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         const unsigned int w0 = rowbase[j * (BXT / 2)], w1 = rowbase[j * (BXT / 2) + 1];
-        const float t0 = (float)(w0 & 0xffffu), t1 = (float)(w0 >> 16), t2 = (float)(w1 & 0xffffu);
-        r[j][0] = t0 + fx * (t1 - t0);
-        r[j][1] = t1 + fx * (t2 - t1);
+        const unsigned int p = __byte_perm(w0, w1, sel01);
+        const float f0 = __uint_as_float(__byte_perm(p, MAG, 0x7610));
+        const float f1 = __uint_as_float(__byte_perm(p, MAG, 0x7632));
+        const float f2 = __uint_as_float(__byte_perm(w1, MAG, sel2));
+        r[j][0] = fmaf(fx, f1 - f0, f0 - 8388608.f);
+        r[j][1] = fmaf(fx, f2 - f1, f1 - 8388608.f);
     }
     c[0] = r[0][0] + fy * (r[1][0] - r[0][0]);
     c[1] = r[0][1] + fy * (r[1][1] - r[0][1]);
@@ -310,34 +324,64 @@ __device__ __forceinline__ void tr_plane(const unsigned int* __restrict__ rowbas
     c[3] = r[1][1] + fy * (r[2][1] - r[1][1]);
 }
 
+// x / y blending factors of a tile's views, computed once per tile by the team (80 values per view: 64 x
+// columns + 16 y rows) into a double-buffered shared table; returns the table to read from
+constexpr int WT_N = TT_X + TT_Y;
+__device__ __forceinline__ const float* team_weights(const FuseArgs2& a, const ViewItem* descs, const TileRec& T, int nst,
+                                                     float* wtab, int& uses, int team, int tid) {
+    float* tab = wtab + (uses & 1) * (NST_T * WT_N);
+    ++uses;
+    const bool ub = a.use_blend != 0;
+    for (int i = tid; i < T.count * WT_N; i += NTEAM) {
+        const int v = i / WT_N, j = i - v * WT_N;
+        const ViewItem& d = descs[(T.it0 + v) % nst];
+        float f = 1.f;
+        if (j < TT_X) {
+            if (!(d.flags & VI_PLAT_X)) f = blend_factor((float)(d.b0[0] + j) + d.o[0], d.dm1[0], d.border[0], d.inv_range[0], ub);
+        } else {
+            if (!(d.flags & VI_PLAT_Y)) f = blend_factor((float)(d.b0[1] + (j - TT_X)) + d.o[1], d.dm1[1], d.border[1], d.inv_range[1], ub);
+        }
+        tab[i] = f;
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(NTEAM) : "memory");
+    return tab;
+}
+
 template <int C, int OUT>
 __device__ __forceinline__ void tr_tile(const FuseArgs2& a, const unsigned char* slots, const ViewItem* descs,
-                                        const TileRec& T, int tid) {
+                                        const TileRec& T, float* wtab, int& uses, int team, int tid) {
     using OT = typename OutT<OUT>::type;
     const int lx = tid & 31, ly = tid >> 5;
-    const bool ub = a.use_blend != 0;
     const unsigned int* base[C];
     const float* wz[C];
+    unsigned int sel01[C], sel2[C];
     float fx[C], fy[C], fz[C], wxy[C][4], prev[C][4];
+    bool need = false;
+#pragma unroll
+    for (int v = 0; v < C; ++v) {
+        const int fl = descs[(T.it0 + v) % NST_T].flags;
+        need = need || (fl & (VI_PLAT_X | VI_PLAT_Y)) != (VI_PLAT_X | VI_PLAT_Y);
+    }
+    const float* tab = nullptr;
+    if (need) tab = team_weights(a, descs, T, NST_T, wtab, uses, team, tid);   // team-uniform branch
 #pragma unroll
     for (int v = 0; v < C; ++v) {
         const int s = (T.it0 + v) % NST_T;
         const ViewItem& d = descs[s];
-        base[v] = reinterpret_cast<const unsigned int*>(slots + (size_t)s * SLOT_T) + (2 * ly) * (BXT / 2) + lx;
+        const int ox = d.b0[0] & 7;            // column of the tile's first tap inside the 8-aligned box
+        base[v] = reinterpret_cast<const unsigned int*>(slots + (size_t)s * SLOT_T) + (2 * ly) * (BXT / 2) + lx + (ox >> 1);
+        sel01[v] = (ox & 1) ? 0x5432u : 0x3210u;
+        sel2[v] = (ox & 1) ? 0x7632u : 0x7610u;
         wz[v] = d.wz;
         fx[v] = d.o[0]; fy[v] = d.o[1]; fz[v] = d.o[2];
         float wx0 = 1.f, wx1 = 1.f, wy0 = 1.f, wy1 = 1.f;
-        if (!(d.flags & VI_PLAT_X)) {
-            const float l = (float)(d.b0[0] + 2 * lx) + fx[v];
-            wx0 = blend_factor(l, d.dm1[0], d.border[0], d.inv_range[0], ub);
-            wx1 = blend_factor((float)(d.b0[0] + 2 * lx + 1) + fx[v], d.dm1[0], d.border[0], d.inv_range[0], ub);
-        }
-        if (!(d.flags & VI_PLAT_Y)) {
-            wy0 = blend_factor((float)(d.b0[1] + 2 * ly) + fy[v], d.dm1[1], d.border[1], d.inv_range[1], ub);
-            wy1 = blend_factor((float)(d.b0[1] + 2 * ly + 1) + fy[v], d.dm1[1], d.border[1], d.inv_range[1], ub);
+        if (need) {
+            const float* tv = tab + v * WT_N;
+            wx0 = tv[2 * lx]; wx1 = tv[2 * lx + 1];
+            wy0 = tv[TT_X + 2 * ly]; wy1 = tv[TT_X + 2 * ly + 1];
         }
         wxy[v][0] = wx0 * wy0; wxy[v][1] = wx1 * wy0; wxy[v][2] = wx0 * wy1; wxy[v][3] = wx1 * wy1;
-        tr_plane(base[v], fx[v], fy[v], prev[v]);
+        tr_plane(base[v], sel01[v], sel2[v], fx[v], fy[v], prev[v]);
     }
     const int x = 2 * lx, y = 2 * ly;
     const bool ok0 = y < T.ny && x < T.nx, ok1 = y + 1 < T.ny && x < T.nx;
@@ -350,7 +394,7 @@ __device__ __forceinline__ void tr_tile(const FuseArgs2& a, const unsigned char*
 #pragma unroll
         for (int v = 0; v < C; ++v) {
             float cur[4];
-            tr_plane(base[v] + (k + 1) * (BYT * BXT / 2), fx[v], fy[v], cur);
+            tr_plane(base[v] + (k + 1) * (BYT * BXT / 2), sel01[v], sel2[v], fx[v], fy[v], cur);
             const float wk = wz[v][k];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -367,7 +411,7 @@ __device__ __forceinline__ void tr_tile(const FuseArgs2& a, const unsigned char*
         }
         if (C > 1) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) res[q] = sw[q] > 0.f ? swi[q] / sw[q] : 0.f;
+            for (int q = 0; q < 4; ++q) res[q] = sw[q] > 0.f ? __fdividef(swi[q], sw[q]) : 0.f;
         }
         OT* p = o0 + (size_t)k * T.pitch_z;
         if (ok0) store_pair<OUT>(a, p, res[0], res[1], has1, vec);
@@ -398,15 +442,15 @@ __device__ __forceinline__ float gather8(const T* __restrict__ d, int dx, int dy
 // output plane recomputed (no per-view register state)
 template <int OUT>
 __device__ __forceinline__ void tr_tile_many(const FuseArgs2& a, const unsigned char* slots, const ViewItem* descs,
-                                             const TileRec& T, int tid) {
+                                             const TileRec& T, float* wtab, int& uses, int team, int tid) {
     using OT = typename OutT<OUT>::type;
     const int lx = tid & 31, ly = tid >> 5;
-    const bool ub = a.use_blend != 0;
     const int x = 2 * lx, y = 2 * ly;
     const bool ok0 = y < T.ny && x < T.nx, ok1 = y + 1 < T.ny && x < T.nx;
     const bool has1 = x + 1 < T.nx;
     OT* o0 = reinterpret_cast<OT*>(T.out) + (size_t)y * T.pitch_y + x;
     const bool vec = ((T.out | ((unsigned long long)T.pitch_y * sizeof(OT)) | ((unsigned long long)T.pitch_z * sizeof(OT))) & (2 * sizeof(OT) - 1)) == 0;
+    const float* tab = team_weights(a, descs, T, NST_T, wtab, uses, team, tid);
 #pragma unroll 1
     for (int k = 0; k < T.nz; ++k) {
         float swi[4] = {0.f, 0.f, 0.f, 0.f}, sw[4] = {0.f, 0.f, 0.f, 0.f};
@@ -415,23 +459,18 @@ __device__ __forceinline__ void tr_tile_many(const FuseArgs2& a, const unsigned 
             const int s = (T.it0 + v) % NST_T;
             const ViewItem& d = descs[s];
             const float wk = d.wz[k];
-            if (wk == 0.f) continue;   // CTA-uniform
+            if (wk == 0.f) continue;   // team-uniform
+            const int ox = d.b0[0] & 7;
+            const unsigned int sel01 = (ox & 1) ? 0x5432u : 0x3210u, sel2 = (ox & 1) ? 0x7632u : 0x7610u;
             const unsigned int* base = reinterpret_cast<const unsigned int*>(slots + (size_t)s * SLOT_T) +
-                                       (k * BYT + 2 * ly) * (BXT / 2) + lx;
+                                       (k * BYT + 2 * ly) * (BXT / 2) + lx + (ox >> 1);
             const float fx = d.o[0], fy = d.o[1], fz = d.o[2];
-            float wx0 = 1.f, wx1 = 1.f, wy0 = 1.f, wy1 = 1.f;
-            if (!(d.flags & VI_PLAT_X)) {
-                wx0 = blend_factor((float)(d.b0[0] + x) + fx, d.dm1[0], d.border[0], d.inv_range[0], ub);
-                wx1 = blend_factor((float)(d.b0[0] + x + 1) + fx, d.dm1[0], d.border[0], d.inv_range[0], ub);
-            }
-            if (!(d.flags & VI_PLAT_Y)) {
-                wy0 = blend_factor((float)(d.b0[1] + y) + fy, d.dm1[1], d.border[1], d.inv_range[1], ub);
-                wy1 = blend_factor((float)(d.b0[1] + y + 1) + fy, d.dm1[1], d.border[1], d.inv_range[1], ub);
-            }
+            const float* tv = tab + v * WT_N;
+            const float wx0 = tv[x], wx1 = tv[x + 1], wy0 = tv[TT_X + y], wy1 = tv[TT_X + y + 1];
             const float wxy[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
             float c0[4], c1[4];
-            tr_plane(base, fx, fy, c0);
-            tr_plane(base + BYT * BXT / 2, fx, fy, c1);
+            tr_plane(base, sel01, sel2, fx, fy, c0);
+            tr_plane(base + BYT * BXT / 2, sel01, sel2, fx, fy, c1);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float val = c0[q] + fz * (c1[q] - c0[q]);
@@ -442,7 +481,7 @@ __device__ __forceinline__ void tr_tile_many(const FuseArgs2& a, const unsigned 
         }
         float res[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) res[q] = sw[q] > 0.f ? swi[q] / sw[q] : 0.f;
+        for (int q = 0; q < 4; ++q) res[q] = sw[q] > 0.f ? __fdividef(swi[q], sw[q]) : 0.f;
         OT* p = o0 + (size_t)k * T.pitch_z;
         if (ok0) store_pair<OUT>(a, p, res[0], res[1], has1, vec);
         if (ok1) store_pair<OUT>(a, p + T.pitch_y, res[2], res[3], has1, vec);
@@ -476,7 +515,7 @@ __device__ __forceinline__ void tr_slow_tile(const FuseArgs2& a, const TileRec& 
                 swi = swi + w * val;
                 sw = sw + w;
             }
-            store1<OUT>(a, obase + (size_t)k * T.pitch_z + (size_t)y * T.pitch_y + x, sw > 0.f ? swi / sw : 0.f);
+            store1<OUT>(a, obase + (size_t)k * T.pitch_z + (size_t)y * T.pitch_y + x, sw > 0.f ? __fdividef(swi, sw) : 0.f);
         }
     }
 }
@@ -559,7 +598,7 @@ __device__ __forceinline__ void gen_tile(const FuseArgs2& a, const unsigned char
         for (int q = 0; q < 4; ++q) {
             const int x = lx + 32 * (q & 1), y = ly + 8 * (q >> 1);
             if (x < T.nx && y < T.ny) {
-                const float res = sw[q] > 0.f ? swi[q] / sw[q] : 0.f;
+                const float res = sw[q] > 0.f ? __fdividef(swi[q], sw[q]) : 0.f;
                 store1<OUT>(a, obase + (size_t)k * T.pitch_z + (size_t)y * T.pitch_y + x, res);
             }
         }
@@ -581,6 +620,9 @@ __device__ __forceinline__ void zero_tile(const FuseArgs2& a, const TileRec& T, 
 // ------------------------------------------------------------------------------------------ the kernel
 extern __shared__ __align__(1024) unsigned char fuse2_smem[];
 
+// Persistent: one CTA per SM; the producer warp draws work records (z-runs of one tile column) from a global
+// counter and streams their tiles through the slot / tile-record rings without ever draining the pipeline;
+// the two consumer teams take alternate tile records until each receives a terminator record.
 template <bool GENERAL, int OUT>
 __global__ void __launch_bounds__(NTHREADS, 1) fuse_tma_kernel(const __grid_constant__ FuseArgs2 a) {
     constexpr int NST = GENERAL ? NST_G : NST_T;
@@ -594,6 +636,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fuse_tma_kernel(const __grid_cons
     unsigned long long* empty = bars + NST;            // [NST]  one team's 8 warps -> producer
     unsigned long long* tfull = bars + 2 * NST;        // [NTR]
     unsigned long long* tempty = bars + 2 * NST + NTR; // [NTR]
+    float* wtab = reinterpret_cast<float*>(bars + 2 * NST + 2 * NTR);   // [NTEAMS][2][NST_T][WT_N]
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (tid == 0) {
@@ -603,75 +646,94 @@ __global__ void __launch_bounds__(NTHREADS, 1) fuse_tma_kernel(const __grid_cons
     }
     __syncthreads();
 
-    const WorkRec W = a.work[blockIdx.x];
-    const BlockDev& B = a.blocks[W.block];
-
     if (wid == NCONS / 32) {
         // ---------------- producer warp: tile records + view items + TMA boxes, in ring order
-        int it = 0;
+        int it = 0, tseq = 0;
         unsigned long long fenced = 0ull;
         const size_t esz = OUT == BS_DTYPE_F32 ? 4 : (OUT == BS_DTYPE_U16 ? 2 : 1);
-        const int tile0 = B.tile_base + (W.tz0 * B.tiles[1] + W.ty) * B.tiles[0] + W.tx;
-        const int tstride = B.tiles[0] * B.tiles[1];
-        TileHdr myh = {0, 0, 0, 0};
-        if (lane < W.ntz) myh = a.hdr[tile0 + lane * tstride];        // ntz <= 32 (host splits longer runs)
-        for (int t = 0; t < W.ntz; ++t) {
-            TileHdr h;
-            h.first = __shfl_sync(0xffffffffu, myh.first, t);
-            h.count = __shfl_sync(0xffffffffu, myh.count, t);
-            h.mode = __shfl_sync(0xffffffffu, myh.mode, t);
-            const int tz = W.tz0 + t;
-            const int tr = t % NTR;
-            mbar_wait(&tempty[tr], ((t / NTR) & 1) ^ 1);
-            if (lane == 0) {
-                TileRec& R = recs[tr];
-                const size_t off = ((size_t)tz * TT_Z * B.size[1] + (size_t)W.ty * TT_Y) * B.size[0] + (size_t)W.tx * TT_X;
-                R.out = (unsigned long long)B.out + off * esz;
-                R.pitch_y = B.size[0];
-                R.pitch_z = (long long)B.size[0] * B.size[1];
-                R.nx = min(TT_X, B.size[0] - W.tx * TT_X);
-                R.ny = min(TT_Y, B.size[1] - W.ty * TT_Y);
-                R.nz = min(TT_Z, B.size[2] - tz * TT_Z);
-                R.count = h.count;
-                R.mode = h.mode;
-                R.it0 = it;
-                R.last = t == W.ntz - 1;
-                R.items = a.pool + h.first;
-            }
-            if (h.mode == 1) {
-                for (int e = 0; e < h.count; ++e, ++it) {
-                    const int s = it % NST;
-                    mbar_wait(&empty[s], ((it / NST) & 1) ^ 1);
-                    const unsigned int* src = reinterpret_cast<const unsigned int*>(a.pool + h.first + e);
-                    unsigned int* dst = reinterpret_cast<unsigned int*>(descs + s);
-                    if (lane < VI_WORDS) dst[lane] = __ldg(src + lane);
-                    __syncwarp();
-                    if (lane == 0) {
-                        const ViewItem& d = descs[s];
-                        const ViewDev& V = a.views[d.view];
-                        const CUtensorMap* tm = GENERAL ? V.tm_g : V.tm_t;
-                        const bool known = d.view < 64 && ((fenced >> d.view) & 1ull);
-                        if (!known) {
-                            tmap_acquire(tm);
-                            if (d.view < 64) fenced |= 1ull << d.view;
+        for (;;) {
+            int w = 0;
+            if (lane == 0) w = atomicAdd(a.work_ctr, 1);
+            w = __shfl_sync(0xffffffffu, w, 0);
+            if (w >= a.nwork) break;
+            const WorkRec W = a.work[w];
+            const BlockDev& B = a.blocks[W.block];
+            const int tile0 = B.tile_base + (W.tz0 * B.tiles[1] + W.ty) * B.tiles[0] + W.tx;
+            const int tstride = B.tiles[0] * B.tiles[1];
+            TileHdr myh = {0, 0, 0, 0};
+            if (lane < W.ntz) myh = a.hdr[tile0 + lane * tstride];        // ntz <= 32 (host splits longer runs)
+            for (int t = 0; t < W.ntz; ++t, ++tseq) {
+                TileHdr h;
+                h.first = __shfl_sync(0xffffffffu, myh.first, t);
+                h.count = __shfl_sync(0xffffffffu, myh.count, t);
+                h.mode = __shfl_sync(0xffffffffu, myh.mode, t);
+                const int tz = W.tz0 + t;
+                const int tr = tseq % NTR;
+                mbar_wait(&tempty[tr], ((tseq / NTR) & 1) ^ 1);
+                if (lane == 0) {
+                    TileRec& R = recs[tr];
+                    const size_t off = ((size_t)tz * TT_Z * B.size[1] + (size_t)W.ty * TT_Y) * B.size[0] + (size_t)W.tx * TT_X;
+                    R.out = (unsigned long long)B.out + off * esz;
+                    R.pitch_y = B.size[0];
+                    R.pitch_z = (long long)B.size[0] * B.size[1];
+                    R.nx = min(TT_X, B.size[0] - W.tx * TT_X);
+                    R.ny = min(TT_Y, B.size[1] - W.ty * TT_Y);
+                    R.nz = min(TT_Z, B.size[2] - tz * TT_Z);
+                    R.count = h.count;
+                    R.mode = h.mode;
+                    R.it0 = it;
+                    R.last = 0;
+                    R.items = a.pool + h.first;
+                }
+                if (h.mode == 1) {
+                    for (int e = 0; e < h.count; ++e, ++it) {
+                        const int s = it % NST;
+                        mbar_wait(&empty[s], ((it / NST) & 1) ^ 1);
+                        const unsigned int* src = reinterpret_cast<const unsigned int*>(a.pool + h.first + e);
+                        unsigned int* dst = reinterpret_cast<unsigned int*>(descs + s);
+                        if (lane < VI_WORDS) dst[lane] = __ldg(src + lane);
+                        __syncwarp();
+                        if (lane == 0) {
+                            const ViewItem& d = descs[s];
+                            const ViewDev& V = a.views[d.view];
+                            const CUtensorMap* tm = GENERAL ? V.tm_g : V.tm_t;
+                            const bool known = d.view < 64 && ((fenced >> d.view) & 1ull);
+                            if (!known) {
+                                tmap_acquire(tm);
+                                if (d.view < 64) fenced |= 1ull << d.view;
+                            }
+                            mbar_expect_tx(&full[s], (GENERAL ? BXG * BYG * BZG : BXT * BYT * BZT) * 2);
+                            tma_load_box(slots + (size_t)s * SLOT, tm, d.b0[0] & ~7, d.b0[1], d.b0[2], &full[s]);
                         }
-                        mbar_expect_tx(&full[s], (GENERAL ? BXG * BYG * BZG : BXT * BYT * BZT) * 2);
-                        tma_load_box(slots + (size_t)s * SLOT, tm, d.b0[0], d.b0[1], d.b0[2], &full[s]);
                     }
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tfull[tr]);
+            }
+        }
+        // one terminator record per team (consecutive sequence numbers cover both parities)
+        for (int g = 0; g < NTEAMS; ++g, ++tseq) {
+            const int tr = tseq % NTR;
+            mbar_wait(&tempty[tr], ((tseq / NTR) & 1) ^ 1);
+            if (lane == 0) {
+                recs[tr].mode = -1;
+                recs[tr].count = 0;
+                mbar_arrive(&tfull[tr]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tfull[tr]);
         }
         return;
     }
 
-    // ---------------- consumer teams: team g renders tiles g, g + 2, ... of the run
+    // ---------------- consumer teams: team g renders tile records g, g + 2, ...
     const int team = tid / NTEAM, ttid = tid % NTEAM;
-    for (int t = team; t < W.ntz; t += NTEAMS) {
-        const int tr = t % NTR;
-        mbar_wait(&tfull[tr], (t / NTR) & 1);
+    float* wt = wtab + team * (2 * NST_T * WT_N);
+    int uses = 0;
+    for (int n = team;; n += NTEAMS) {
+        const int tr = n % NTR;
+        mbar_wait(&tfull[tr], (n / NTR) & 1);
         const TileRec T = recs[tr];
+        if (T.mode < 0) break;
         if (T.mode == 1) {
             for (int v = 0; v < T.count; ++v) {
                 const int it = T.it0 + v;
@@ -684,11 +746,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) fuse_tma_kernel(const __grid_cons
             gen_tile<OUT>(a, slots, descs, T, ttid);
         } else if (T.mode == 1) {
             switch (T.count) {
-                case 1: tr_tile<1, OUT>(a, slots, descs, T, ttid); break;
-                case 2: tr_tile<2, OUT>(a, slots, descs, T, ttid); break;
-                case 3: tr_tile<3, OUT>(a, slots, descs, T, ttid); break;
-                case 4: tr_tile<4, OUT>(a, slots, descs, T, ttid); break;
-                default: tr_tile_many<OUT>(a, slots, descs, T, ttid); break;
+                case 1: tr_tile<1, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
+                case 2: tr_tile<2, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
+                case 3: tr_tile<3, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
+                case 4: tr_tile<4, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
+                default: tr_tile_many<OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
             }
         } else {
             tr_slow_tile<OUT>(a, T, ttid);
@@ -787,7 +849,8 @@ void launch_kernel(int out_dtype, int grid, size_t smem, cudaStream_t s, const F
 
 constexpr size_t smem_bytes(bool general) {
     return (size_t)(general ? NST_G * SLOT_G : NST_T * SLOT_T) + (size_t)(general ? NST_G : NST_T) * sizeof(ViewItem) +
-           NTR * sizeof(TileRec) + (2 * (general ? NST_G : NST_T) + 2 * NTR) * 8 + 1024;
+           NTR * sizeof(TileRec) + (2 * (general ? NST_G : NST_T) + 2 * NTR) * 8 +
+           (size_t)NTEAMS * 2 * NST_T * WT_N * sizeof(float) + 1024;
 }
 
 bool eligible(bs_ctx* ctx, const bs_view* views, int n_views, const bs_fuse_params* p) {
@@ -974,13 +1037,16 @@ int fuse2_launch(bs_ctx* ctx, const bs_view* views, int n_views, int nb, const l
     a.hdr = (const TileHdr*)W->hdr;
     a.pool = (const ViewItem*)W->pool;
     a.use_blend = use_blend;
+    a.work_ctr = W->ctr + 2;
+    a.nwork = (int)work.size();
     a.ctop = p->out_dtype == BS_DTYPE_U8 ? 255.0 : 65535.0;
     a.cmin = p->min_intensity;
     a.cscale = p->out_dtype == BS_DTYPE_F32 ? 1.0 : a.ctop / (p->max_intensity - p->min_intensity);
     {
         bs_launch_scope scope(ctx, "fuse");
-        if (general) launch_kernel<true>(p->out_dtype, (int)work.size(), smem_bytes(true), ctx->stream, a);
-        else launch_kernel<false>(p->out_dtype, (int)work.size(), smem_bytes(false), ctx->stream, a);
+        const int grid = (int)std::min<size_t>(work.size(), (size_t)ctx->sm_count);
+        if (general) launch_kernel<true>(p->out_dtype, grid, smem_bytes(true), ctx->stream, a);
+        else launch_kernel<false>(p->out_dtype, grid, smem_bytes(false), ctx->stream, a);
     }
     BS_CUDA(ctx, cudaGetLastError());
     {
