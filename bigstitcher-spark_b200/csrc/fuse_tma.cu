@@ -299,6 +299,16 @@ __device__ __forceinline__ void store_pair(const FuseArgs2& a, typename OutT<OUT
     }
 }
 
+// sum(w I) / sum(w): one MUFU.RCP + FMUL (2 ulp) for ordinary weights, IEEE division for denormal-range sums
+__device__ __forceinline__ float wdiv(float swi, float sw) {
+    if (sw > 1e-30f) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(sw));
+        return swi * r;
+    }
+    return sw > 0.f ? swi / sw : 0.f;
+}
+
 // ------------------------------------------------------------------------------------------ translation tile
 // one z plane of the staged box -> the thread's 2 x 2 x/y-interpolated values (x then y, a + f (b - a)).
 // uint16 -> float without the conversion pipe: PRMT builds 0x4B00hhll = 2^23 + v, differences of two such
@@ -347,7 +357,8 @@ __device__ __forceinline__ const float* team_weights(const FuseArgs2& a, const V
     return tab;
 }
 
-template <int C, int OUT>
+// PLAT (C == 1 only): the single view's weight is 1 on the whole tile -> the voxel is the sample itself
+template <int C, int OUT, bool PLAT = false>
 __device__ __forceinline__ void tr_tile(const FuseArgs2& a, const unsigned char* slots, const ViewItem* descs,
                                         const TileRec& T, float* wtab, int& uses, int team, int tid) {
     using OT = typename OutT<OUT>::type;
@@ -399,8 +410,9 @@ __device__ __forceinline__ void tr_tile(const FuseArgs2& a, const unsigned char*
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float val = prev[v][q] + fz[v] * (cur[q] - prev[v][q]);
-                const float w = wxy[v][q] * wk;
                 prev[v][q] = cur[q];
+                if (PLAT) { res[q] = val; continue; }
+                const float w = wxy[v][q] * wk;
                 if (C == 1) {
                     res[q] = w > 0.f ? val : 0.f;
                 } else {
@@ -411,7 +423,7 @@ __device__ __forceinline__ void tr_tile(const FuseArgs2& a, const unsigned char*
         }
         if (C > 1) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) res[q] = sw[q] > 0.f ? __fdividef(swi[q], sw[q]) : 0.f;
+            for (int q = 0; q < 4; ++q) res[q] = wdiv(swi[q], sw[q]);
         }
         OT* p = o0 + (size_t)k * T.pitch_z;
         if (ok0) store_pair<OUT>(a, p, res[0], res[1], has1, vec);
@@ -481,7 +493,7 @@ __device__ __forceinline__ void tr_tile_many(const FuseArgs2& a, const unsigned 
         }
         float res[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) res[q] = sw[q] > 0.f ? __fdividef(swi[q], sw[q]) : 0.f;
+        for (int q = 0; q < 4; ++q) res[q] = wdiv(swi[q], sw[q]);
         OT* p = o0 + (size_t)k * T.pitch_z;
         if (ok0) store_pair<OUT>(a, p, res[0], res[1], has1, vec);
         if (ok1) store_pair<OUT>(a, p + T.pitch_y, res[2], res[3], has1, vec);
@@ -515,7 +527,7 @@ __device__ __forceinline__ void tr_slow_tile(const FuseArgs2& a, const TileRec& 
                 swi = swi + w * val;
                 sw = sw + w;
             }
-            store1<OUT>(a, obase + (size_t)k * T.pitch_z + (size_t)y * T.pitch_y + x, sw > 0.f ? __fdividef(swi, sw) : 0.f);
+            store1<OUT>(a, obase + (size_t)k * T.pitch_z + (size_t)y * T.pitch_y + x, wdiv(swi, sw));
         }
     }
 }
@@ -562,10 +574,12 @@ __device__ __forceinline__ void gen_tile(const FuseArgs2& a, const unsigned char
                     const float ax = rx + b0x, ay = ry + b0y, az = rz + b0z;   // absolute source coordinate
                     if (!inside_all)
                         ok = ax >= 0.f && ax <= d.dm1[0] && ay >= 0.f && ay <= d.dm1[1] && az >= 0.f && az <= d.dm1[2];
-                    if (ok && ub && !plateau)
-                        ok = blend_axis(ax, d.dm1[0], d.border[0], d.inv_range[0], 0, nullptr, w) &&
-                             blend_axis(ay, d.dm1[1], d.border[1], d.inv_range[1], 0, nullptr, w) &&
-                             blend_axis(az, d.dm1[2], d.border[2], d.inv_range[2], 0, nullptr, w);
+                    if (ok && ub && !plateau) {
+                        // per-axis plateau flags: a tile in a one-axis overlap zone evaluates one cosine, not three
+                        if (!(flags & VI_PLAT_X)) ok = blend_axis(ax, d.dm1[0], d.border[0], d.inv_range[0], 0, nullptr, w);
+                        if (ok && !(flags & VI_PLAT_Y)) ok = blend_axis(ay, d.dm1[1], d.border[1], d.inv_range[1], 0, nullptr, w);
+                        if (ok && !(flags & VI_PLAT_Z)) ok = blend_axis(az, d.dm1[2], d.border[2], d.inv_range[2], 0, nullptr, w);
+                    }
                     if (!inside_all) {   // keep the taps of masked voxels inside the staged box
                         rx = fminf(fmaxf(rx, 0.f), (float)(BXG - 2));
                         ry = fminf(fmaxf(ry, 0.f), (float)(BYG - 2));
@@ -598,7 +612,7 @@ __device__ __forceinline__ void gen_tile(const FuseArgs2& a, const unsigned char
         for (int q = 0; q < 4; ++q) {
             const int x = lx + 32 * (q & 1), y = ly + 8 * (q >> 1);
             if (x < T.nx && y < T.ny) {
-                const float res = sw[q] > 0.f ? __fdividef(swi[q], sw[q]) : 0.f;
+                const float res = wdiv(swi[q], sw[q]);
                 store1<OUT>(a, obase + (size_t)k * T.pitch_z + (size_t)y * T.pitch_y + x, res);
             }
         }
@@ -746,7 +760,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) fuse_tma_kernel(const __grid_cons
             gen_tile<OUT>(a, slots, descs, T, ttid);
         } else if (T.mode == 1) {
             switch (T.count) {
-                case 1: tr_tile<1, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
+                case 1:
+                    if ((descs[T.it0 % NST].flags & (VI_PLAT_X | VI_PLAT_Y | VI_PLAT_Z)) == (VI_PLAT_X | VI_PLAT_Y | VI_PLAT_Z))
+                        tr_tile<1, OUT, true>(a, slots, descs, T, wt, uses, team, ttid);
+                    else
+                        tr_tile<1, OUT>(a, slots, descs, T, wt, uses, team, ttid);
+                    break;
                 case 2: tr_tile<2, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
                 case 3: tr_tile<3, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
                 case 4: tr_tile<4, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
