@@ -900,29 +900,6 @@ typedef FftStatic<540, 3, 8, 1, PCM_THREADS, 9, 10, 6> FftS540;
 typedef FftStatic<540, 2, 4, 1, PCM_THREADS, 9, 10, 6> FftS540T4;
 typedef FftStatic<540, 3, 8, 1, PCM_THREADS, 27, 20> FftS540R2;   // two-stage variant (radix 27 x 20)
 
-struct GatherArgs {
-    const float* pcm;
-    int Px, Py, Pz;
-    long long rowpitch;
-    int K;
-    const long long* idx;  // K linear indices (z*Py + y)*Px + x, or -1
-    float* out;            // K * 27
-};
-
-__global__ void k_gather27(const __grid_constant__ GatherArgs a) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.K * 27) return;
-    const int p = t / 27, o = t - p * 27;
-    const long long li = a.idx[p];
-    if (li < 0) { a.out[t] = 0.f; return; }
-    const int x = (int)(li % a.Px);
-    const long long r = li / a.Px;
-    const int y = (int)(r % a.Py), z = (int)(r / a.Py);
-    const int dz = o / 9 - 1, dy = (o / 3) % 3 - 1, dx = o % 3 - 1;
-    const int xx = (x + dx + a.Px) % a.Px, yy = (y + dy + a.Py) % a.Py, zz = (z + dz + a.Pz) % a.Pz;
-    a.out[t] = a.pcm[((long long)zz * a.Py + yy) * a.rowpitch + xx];
-}
-
 // ------------------------------------------------------------------------------------------
 // Pearson sums for all candidate shifts in one launch
 struct PearsonCand {
@@ -1090,7 +1067,9 @@ __device__ __forceinline__ void pearson_generic(const PearsonArgs& a, int ncand,
 }
 
 // dynamic smem: 5 accumulators per candidate (8 bytes each)
-__global__ void __launch_bounds__(PCM_THREADS) k_pearson(const __grid_constant__ PearsonArgs a, int ncand) {
+__global__ void __launch_bounds__(PCM_THREADS) k_pearson(const __grid_constant__ PearsonArgs a, const int* __restrict__ ncand_ptr) {
+    const int ncand = *ncand_ptr;     // written by k_pcm_select (no host round trip between peaks and Pearson)
+    if (ncand <= 0) return;
     unsigned long long* s_u = reinterpret_cast<unsigned long long*>(bs_sm);
     double* s_d = reinterpret_cast<double*>(bs_sm);
     for (int i = threadIdx.x; i < 5 * ncand; i += blockDim.x) s_u[i] = 0ull;  // 0.0 has the same bit pattern
@@ -1103,6 +1082,137 @@ __global__ void __launch_bounds__(PCM_THREADS) k_pearson(const __grid_constant__
         if (a.dtype == BS_DTYPE_F32) { if (s_d[i] != 0.0) atomicAdd(a.sums_d + i, s_d[i]); }
         else if (s_u[i]) atomicAdd(a.sums_u + i, s_u[i]);
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Device-side glue between peak search and Pearson verification: merge the per-CTA top-K lists, expand every
+// peak into its 2^3 wrap candidates (PhaseCorrelation2Util.expandPeakToPossibleShifts for equal-size crops),
+// keep those with enough overlap, gather the 3x3x3 neighbourhoods for the sub-pixel fit.  One small CTA; the
+// host reads ONE result block per pair, after the Pearson kernel, and can do so a pair late.
+struct PcmSelect {
+    int np;                       // peaks kept (<= K)
+    int nslots;                   // Pearson-verified candidates
+    long long idx[PCM_KMAX];      // linear PCM index of peak i
+    float val[PCM_KMAX];
+    float nb[27 * PCM_KMAX];      // periodic 3x3x3 neighbourhoods
+};
+
+// candidate i (0..7) of a peak at PCM location loc: shift per axis is loc or loc - P; returns true when the
+// candidate overlaps by at least min_px voxels (then pc / npx describe the overlap boxes)
+__host__ __device__ inline bool pcm_expand_candidate(const long long loc[3], const int P[3], const int d[3], int i,
+                                                     long long min_px, long long shift[3], PearsonCand* pc, long long* npx_out) {
+    bool overlap = true;
+    long long npx = 1;
+    for (int a = 0; a < 3; ++a) {
+        long long s = loc[a];
+        if (((i >> a) & 1) == 0) s = s < 0 ? s + P[a] : s - P[a];
+        shift[a] = s;
+        const long long n = d[a];
+        if (s >= 0) {
+            if (s >= n) { overlap = false; continue; }
+            pc->o1[a] = (int)s; pc->o2[a] = 0; pc->sz[a] = (int)(n - s < n ? n - s : n);
+        } else {
+            if (s <= -n) { overlap = false; continue; }
+            pc->o1[a] = 0; pc->o2[a] = (int)-s; pc->sz[a] = (int)(n + s < n ? n + s : n);
+        }
+        npx *= pc->sz[a];
+    }
+    pc->pad = 0;
+    *npx_out = npx;
+    return overlap && npx >= min_px;
+}
+
+struct SelectArgs {
+    const PeakEntry* peaks;       // n_entries per-CTA candidates (idx < 0: empty)
+    int n_entries;
+    int K;
+    int P[3], d[3];
+    long long rowpitch;
+    const float* pcm;
+    long long min_px;
+    int do_subpixel;
+    PcmSelect* sel;
+    PearsonCand* cands;           // 8 * K
+    unsigned long long* sums;     // 5 * 8 * K, zeroed here
+    int* ncand;
+};
+
+__global__ void __launch_bounds__(256) k_pcm_select(const __grid_constant__ SelectArgs a) {
+    __shared__ float s_v[8];
+    __shared__ long long s_i[8];
+    __shared__ float s_pv[PCM_KMAX];
+    __shared__ long long s_pi[PCM_KMAX];
+    __shared__ int s_np, s_nslots;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    float lastv = INFINITY;
+    long long lasti = -1;
+    int np = 0;
+    for (int j = 0; j < a.K; ++j) {
+        // best entry that comes strictly after the previous pick in (value desc, index asc) order
+        float bv = -INFINITY;
+        long long bi = LLONG_MAX;
+        for (int e = tid; e < a.n_entries; e += blockDim.x) {
+            const PeakEntry pe = a.peaks[e];
+            if (pe.idx < 0) continue;
+            if (!peak_better(lastv, lasti, pe.val, pe.idx)) continue;
+            if (bi == LLONG_MAX || peak_better(pe.val, pe.idx, bv, bi)) { bv = pe.val; bi = pe.idx; }
+        }
+        for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_down_sync(0xffffffffu, bv, o);
+            const long long oi = __shfl_down_sync(0xffffffffu, bi, o);
+            if (oi != LLONG_MAX && (bi == LLONG_MAX || peak_better(ov, oi, bv, bi))) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_v[wid] = bv; s_i[wid] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+                if (s_i[w] != LLONG_MAX && (bi == LLONG_MAX || peak_better(s_v[w], s_i[w], bv, bi))) { bv = s_v[w]; bi = s_i[w]; }
+            s_v[0] = bv; s_i[0] = bi;
+        }
+        __syncthreads();
+        bv = s_v[0]; bi = s_i[0];
+        __syncthreads();
+        if (bi == LLONG_MAX) break;
+        if (tid == 0) { s_pv[np] = bv; s_pi[np] = bi; }
+        lastv = bv; lasti = bi;
+        ++np;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        int nslots = 0;
+        for (int pi = 0; pi < np; ++pi) {
+            const long long li = s_pi[pi];
+            const long long loc[3] = {li % a.P[0], (li / a.P[0]) % a.P[1], li / ((long long)a.P[0] * a.P[1])};
+            for (int i = 0; i < 8; ++i) {
+                long long shift[3], npx;
+                PearsonCand pc;
+                pc.o1[0] = pc.o1[1] = pc.o1[2] = pc.o2[0] = pc.o2[1] = pc.o2[2] = pc.sz[0] = pc.sz[1] = pc.sz[2] = 0;
+                if (pcm_expand_candidate(loc, a.P, a.d, i, a.min_px, shift, &pc, &npx)) a.cands[nslots++] = pc;
+            }
+        }
+        a.sel->np = np;
+        a.sel->nslots = nslots;
+        *a.ncand = nslots;
+        s_np = np; s_nslots = nslots;
+    }
+    __syncthreads();
+    np = s_np;
+    for (int i = tid; i < PCM_KMAX; i += blockDim.x) {
+        a.sel->idx[i] = i < np ? s_pi[i] : -1;
+        a.sel->val[i] = i < np ? s_pv[i] : 0.f;
+    }
+    for (int i = tid; i < 5 * s_nslots; i += blockDim.x) a.sums[i] = 0ull;
+    if (a.do_subpixel)
+        for (int t = tid; t < 27 * np; t += blockDim.x) {
+            const int p = t / 27, o = t - p * 27;
+            const long long li = s_pi[p];
+            const int x = (int)(li % a.P[0]);
+            const long long r = li / a.P[0];
+            const int y = (int)(r % a.P[1]), z = (int)(r / a.P[1]);
+            const int dz = o / 9 - 1, dy = (o / 3) % 3 - 1, dx = o % 3 - 1;
+            const int xx = (x + dx + a.P[0]) % a.P[0], yy = (y + dy + a.P[1]) % a.P[1], zz = (z + dz + a.P[2]) % a.P[2];
+            a.sel->nb[t] = a.pcm[((long long)zz * a.P[1] + yy) * a.rowpitch + xx];
+        }
 }
 
 // ==========================================================================================
@@ -1200,7 +1310,9 @@ static PcmDeviceTables* tables_of(bs_ctx* ctx) {
     return (PcmDeviceTables*)ctx->ws.tables;
 }
 
+void bs_pcm_slots_free(bs_ctx* ctx);
 void bs_pcm_workspace_free(bs_ctx* ctx) {
+    bs_pcm_slots_free(ctx);
     bs_pcm_workspace& ws = ctx->ws;
     if (ws.spec_a) cudaFree(ws.spec_a);
     if (ws.spec_b) cudaFree(ws.spec_b);
@@ -1317,7 +1429,7 @@ static int pcm_workspace(bs_ctx* ctx, const PcmGeometry& g) {
         BS_CUDA(ctx, cudaMalloc(&ws.spec_b, need));
         ws.spec_bytes = need;
     }
-    const size_t small_need = 1 << 20;
+    const size_t small_need = 4 << 20;   // PCM_SLOTS result slots (per-CTA peak lists, select block, candidates, sums)
     if (!ws.small) {
         BS_CUDA(ctx, cudaMalloc(&ws.small, small_need));
         BS_CUDA(ctx, cudaHostAlloc(&ws.small_host, small_need, cudaHostAllocDefault));
@@ -1575,40 +1687,83 @@ static double pearson_from_dbl_sums(const double s[5], long long n) {
 }
 
 // full pipeline on device-resident crops
-static int pcm_run(bs_ctx* ctx, const void* d1, const void* d2, const long long dims[3], int dtype,
-                   const bs_pcm_params* p, bs_pcm_result* out) {
-    memset(out, 0, sizeof(*out));
-    out->r = -INFINITY;
+// Result slots: a pair's device-side result block (peaks, neighbourhoods, candidates, Pearson sums) is read
+// back by ONE async copy; the host math of pair i (r from integer sums, candidate sort, sub-pixel solve) runs
+// after pair i+1 has been enqueued, so the stream never drains between pairs.
+#define PCM_SLOTS 2
+struct PcmPending {
+    bool active = false;
+    PcmGeometry g;
+    bs_pcm_params p;
+    int dtype = 0;
+    long long min_px = 0;
+    size_t off_sel = 0, off_cands = 0, off_sums = 0, slot_base = 0;
+};
+
+struct PcmSlotState {
+    PcmPending pend[PCM_SLOTS];
+    cudaEvent_t done[PCM_SLOTS] = {};
+};
+static std::mutex g_slot_mu;
+static std::unordered_map<bs_ctx*, PcmSlotState*> g_slot_states;
+static PcmSlotState* slots_of(bs_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    auto it = g_slot_states.find(ctx);
+    if (it != g_slot_states.end()) return it->second;
+    PcmSlotState* s = new PcmSlotState();
+    g_slot_states[ctx] = s;
+    return s;
+}
+void bs_pcm_slots_free(bs_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(g_slot_mu);
+    auto it = g_slot_states.find(ctx);
+    if (it == g_slot_states.end()) return;
+    for (int i = 0; i < PCM_SLOTS; ++i)
+        if (it->second->done[i]) cudaEventDestroy(it->second->done[i]);
+    delete it->second;
+    g_slot_states.erase(it);
+}
+
+static int pcm_check_params(bs_ctx* ctx, const bs_pcm_params* p, int dtype) {
     if (p->peaks_to_check < 1 || p->peaks_to_check > PCM_KMAX)
         return bs_set_error(ctx, BS_ERR_ARG, "pcm: peaks_to_check must be in [1,%d]", PCM_KMAX);
     if (p->interpolate_xcorr)
         return bs_set_error(ctx, BS_ERR_UNSUPPORTED, "pcm: interpolate_xcorr is not supported (reference default false)");
     if (dtype != BS_DTYPE_U16 && dtype != BS_DTYPE_F32 && dtype != BS_DTYPE_U8)
         return bs_set_error(ctx, BS_ERR_ARG, "pcm: bad dtype %d", dtype);
-    PcmGeometry g;
-    int rc = pcm_geometry(ctx, dims, p->extension, &g);
+    return BS_OK;
+}
+
+// everything of one pair that runs on the device, asynchronously, into result slot `slot`
+static int pcm_enqueue(bs_ctx* ctx, const void* d1, const void* d2, const long long dims[3], int dtype,
+                       const bs_pcm_params* p, int slot) {
+    int rc = pcm_check_params(ctx, p, dtype);
     if (rc) return rc;
+    PcmSlotState* S = slots_of(ctx);
+    PcmPending& pd = S->pend[slot];
+    if ((rc = pcm_geometry(ctx, dims, p->extension, &pd.g))) return rc;
+    const PcmGeometry& g = pd.g;
     PcmDeviceTables* t;
     if ((rc = pcm_tables(ctx, g, &t))) return rc;
     if ((rc = pcm_workspace(ctx, g))) return rc;
     if ((rc = pcm_compute_pcm(ctx, d1, d2, dtype, g, t))) return rc;
-    for (int d = 0; d < 3; ++d) out->pad[d] = g.P[d];
 
     bs_pcm_workspace& ws = ctx->ws;
     const int K = p->peaks_to_check;
     const int peak_ctas = std::max(1, std::min(ctx->sm_count * 8, (g.P[1] * g.P[2] + 7) / 8));
-    // small-buffer layout (device and pinned mirror share offsets)
-    unsigned char* dsmall = (unsigned char*)ws.small;
-    unsigned char* hsmall = (unsigned char*)ws.small_host;
+    // small-buffer layout of one slot (device and pinned mirror share offsets)
+    const size_t slot_bytes = ws.small_bytes / PCM_SLOTS;
+    pd.slot_base = (size_t)slot * slot_bytes;
     size_t off = 0;
+    pd.off_sel = off;   off += (sizeof(PcmSelect) + 15) & ~(size_t)15;
+    pd.off_cands = off; off += sizeof(PearsonCand) * 8 * PCM_KMAX;
+    pd.off_sums = off;  off += sizeof(unsigned long long) * 5 * 8 * PCM_KMAX;
+    const size_t readback = off;
+    const size_t off_ncand = off; off += 16;
     const size_t off_peaks = off; off += sizeof(PeakEntry) * (size_t)peak_ctas * K;
-    const size_t off_idx = off;   off += sizeof(long long) * PCM_KMAX;
-    const size_t off_nb = off;    off += sizeof(float) * 27 * PCM_KMAX;
-    off = (off + 15) & ~(size_t)15;
-    const size_t off_cands = off; off += sizeof(PearsonCand) * 8 * PCM_KMAX;
-    const size_t off_sums = off;  off += sizeof(unsigned long long) * 5 * 8 * PCM_KMAX;
-    if (off > ws.small_bytes) return bs_set_error(ctx, BS_ERR_NOMEM, "pcm: scratch too small");
-
+    if (off > slot_bytes) return bs_set_error(ctx, BS_ERR_NOMEM, "pcm: scratch too small");
+    unsigned char* dsmall = (unsigned char*)ws.small + pd.slot_base;
+    unsigned char* hsmall = (unsigned char*)ws.small_host + pd.slot_base;
     {
         PeakArgs a;
         a.pcm = (const float*)ws.spec_a;
@@ -1620,45 +1775,71 @@ static int pcm_run(bs_ctx* ctx, const void* d1, const void* d2, const long long 
         k_peaks<<<peak_ctas, PCM_THREADS, 0, ctx->stream>>>(a);
     }
     BS_CUDA(ctx, cudaGetLastError());
-    BS_CUDA(ctx, cudaMemcpyAsync(hsmall + off_peaks, dsmall + off_peaks, sizeof(PeakEntry) * (size_t)peak_ctas * K,
-                                 cudaMemcpyDeviceToHost, ctx->stream));
-    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    std::vector<PeakEntry> peaks((PeakEntry*)(hsmall + off_peaks), (PeakEntry*)(hsmall + off_peaks) + (size_t)peak_ctas * K);
-    peaks.erase(std::remove_if(peaks.begin(), peaks.end(), [](const PeakEntry& e) { return e.idx < 0; }), peaks.end());
-    std::sort(peaks.begin(), peaks.end(), [](const PeakEntry& x, const PeakEntry& y) {
-        return x.val > y.val || (x.val == y.val && x.idx < y.idx);
-    });
-    if ((int)peaks.size() > K) peaks.resize(K);
-    const int np = (int)peaks.size();
-    if (np == 0) return BS_OK;  // found = 0
-
-    long long* hidx = (long long*)(hsmall + off_idx);
-    for (int i = 0; i < PCM_KMAX; ++i) hidx[i] = i < np ? peaks[i].idx : -1;
-    if (p->do_subpixel) {
-        BS_CUDA(ctx, cudaMemcpyAsync(dsmall + off_idx, hidx, sizeof(long long) * PCM_KMAX, cudaMemcpyHostToDevice, ctx->stream));
-        GatherArgs a;
-        a.pcm = (const float*)ws.spec_a;
-        a.Px = g.P[0]; a.Py = g.P[1]; a.Pz = g.P[2];
-        a.rowpitch = 2LL * g.pitch;
-        a.K = np;
-        a.idx = (const long long*)(dsmall + off_idx);
-        a.out = (float*)(dsmall + off_nb);
-        {
-            bs_launch_scope sc(ctx, "gather27");
-            k_gather27<<<(np * 27 + 127) / 128, 128, 0, ctx->stream>>>(a);
-        }
-        BS_CUDA(ctx, cudaGetLastError());
-        BS_CUDA(ctx, cudaMemcpyAsync(hsmall + off_nb, dsmall + off_nb, sizeof(float) * 27 * np, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-
-    // candidate expansion (PhaseCorrelation2Util.expandPeakToPossibleShifts, equal-size crops)
     const long long n_px = (long long)g.d[0] * g.d[1] * g.d[2];
-    const long long min_px = (long long)((double)n_px * p->min_overlap_frac);
+    pd.min_px = (long long)((double)n_px * p->min_overlap_frac);
+    pd.p = *p;
+    pd.dtype = dtype;
+    {
+        SelectArgs a;
+        a.peaks = (const PeakEntry*)(dsmall + off_peaks);
+        a.n_entries = peak_ctas * K;
+        a.K = K;
+        for (int d = 0; d < 3; ++d) { a.P[d] = g.P[d]; a.d[d] = g.d[d]; }
+        a.rowpitch = 2LL * g.pitch;
+        a.pcm = (const float*)ws.spec_a;
+        a.min_px = pd.min_px;
+        a.do_subpixel = p->do_subpixel ? 1 : 0;
+        a.sel = (PcmSelect*)(dsmall + pd.off_sel);
+        a.cands = (PearsonCand*)(dsmall + pd.off_cands);
+        a.sums = (unsigned long long*)(dsmall + pd.off_sums);
+        a.ncand = (int*)(dsmall + off_ncand);
+        bs_launch_scope sc(ctx, "select");
+        k_pcm_select<<<1, 256, 0, ctx->stream>>>(a);
+    }
+    BS_CUDA(ctx, cudaGetLastError());
+    {
+        PearsonArgs a;
+        a.img1 = d1; a.img2 = d2;
+        a.dtype = dtype;
+        a.dx = g.d[0]; a.dy = g.d[1]; a.dz = g.d[2];
+        a.cands = (const PearsonCand*)(dsmall + pd.off_cands);
+        a.sums_u = (unsigned long long*)(dsmall + pd.off_sums);
+        a.sums_d = (double*)(dsmall + pd.off_sums);
+        const long long rows = (long long)g.d[1] * g.d[2];
+        const long long chunks = (rows + PR_ROWS - 1) / PR_ROWS;
+        const int ctas = (int)std::max<long long>(1, std::min<long long>((chunks + 7) / 8, (long long)ctx->sm_count * 8));
+        bs_launch_scope sc(ctx, "pearson");
+        k_pearson<<<ctas, PCM_THREADS, sizeof(unsigned long long) * 5 * 8 * K, ctx->stream>>>(a, (const int*)(dsmall + off_ncand));
+    }
+    BS_CUDA(ctx, cudaGetLastError());
+    BS_CUDA(ctx, cudaMemcpyAsync(hsmall, dsmall, readback, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!S->done[slot]) BS_CUDA(ctx, cudaEventCreateWithFlags(&S->done[slot], cudaEventDisableTiming));
+    BS_CUDA(ctx, cudaEventRecord(S->done[slot], ctx->stream));
+    pd.active = true;
+    return BS_OK;
+}
+
+// host half of a pair: wait for its result block, derive r, sort the candidates, solve the sub-pixel fit
+static int pcm_finish(bs_ctx* ctx, int slot, bs_pcm_result* out) {
+    PcmSlotState* S = slots_of(ctx);
+    PcmPending& pd = S->pend[slot];
+    memset(out, 0, sizeof(*out));
+    out->r = -INFINITY;
+    if (!pd.active) return bs_set_error(ctx, BS_ERR_ARG, "pcm: no pending pair in slot %d", slot);
+    pd.active = false;
+    BS_CUDA(ctx, cudaEventSynchronize(S->done[slot]));
+    const PcmGeometry& g = pd.g;
+    for (int d = 0; d < 3; ++d) out->pad[d] = g.P[d];
+    const unsigned char* hsmall = (const unsigned char*)ctx->ws.small_host + pd.slot_base;
+    const PcmSelect* sel = (const PcmSelect*)(hsmall + pd.off_sel);
+    const unsigned long long* hsums = (const unsigned long long*)(hsmall + pd.off_sums);
+    const int np = sel->np;
+    if (np == 0) return BS_OK;  // found = 0
+    // same enumeration as k_pcm_select: slots are numbered in (peak, candidate) order
     std::vector<HostCand> cands;
-    PearsonCand* hc = (PearsonCand*)(hsmall + off_cands);
     int nslots = 0;
     for (int pi = 0; pi < np; ++pi) {
-        const long long li = peaks[pi].idx;
+        const long long li = sel->idx[pi];
         const long long loc[3] = {li % g.P[0], (li / g.P[0]) % g.P[1], li / ((long long)g.P[0] * g.P[1])};
         for (int i = 0; i < 8; ++i) {
             HostCand c;
@@ -1667,59 +1848,23 @@ static int pcm_run(bs_ctx* ctx, const void* d1, const void* d2, const long long 
             c.r = -INFINITY;
             c.npx = 0;
             c.slot = -1;
-            bool overlap = true;
             PearsonCand pc;
             memset(&pc, 0, sizeof(pc));
-            long long npx = 1;
-            for (int d = 0; d < 3; ++d) {
-                long long s = loc[d];
-                if (((i >> d) & 1) == 0) s = s < 0 ? s + g.P[d] : s - g.P[d];
-                c.shift[d] = s;
-                const long long n = g.d[d];
-                if (s >= 0) {
-                    if (s >= n) { overlap = false; continue; }
-                    pc.o1[d] = (int)s; pc.o2[d] = 0; pc.sz[d] = (int)std::min(n - s, n);
-                } else {
-                    if (s <= -n) { overlap = false; continue; }
-                    pc.o1[d] = 0; pc.o2[d] = (int)-s; pc.sz[d] = (int)std::min(n + s, n);
-                }
-                npx *= pc.sz[d];
-            }
-            if (overlap && npx >= min_px) {
+            long long npx = 0;
+            if (pcm_expand_candidate(loc, g.P, g.d, i, pd.min_px, c.shift, &pc, &npx)) {
                 out->pearson_px += npx;
                 c.npx = npx;
-                c.slot = nslots;
-                hc[nslots++] = pc;
+                c.slot = nslots++;
             }
             cands.push_back(c);
         }
     }
+    if (nslots != sel->nslots)
+        return bs_set_error(ctx, BS_ERR_CUDA, "pcm: candidate enumeration mismatch (host %d, device %d)", nslots, sel->nslots);
     out->n_candidates = nslots;
-    unsigned long long* hsums = (unsigned long long*)(hsmall + off_sums);
-    if (nslots > 0) {
-        BS_CUDA(ctx, cudaMemcpyAsync(dsmall + off_cands, hc, sizeof(PearsonCand) * nslots, cudaMemcpyHostToDevice, ctx->stream));
-        BS_CUDA(ctx, cudaMemsetAsync(dsmall + off_sums, 0, sizeof(unsigned long long) * 5 * nslots, ctx->stream));
-        PearsonArgs a;
-        a.img1 = d1; a.img2 = d2;
-        a.dtype = dtype;
-        a.dx = g.d[0]; a.dy = g.d[1]; a.dz = g.d[2];
-        a.cands = (const PearsonCand*)(dsmall + off_cands);
-        a.sums_u = (unsigned long long*)(dsmall + off_sums);
-        a.sums_d = (double*)(dsmall + off_sums);
-        const long long rows = (long long)g.d[1] * g.d[2];
-        const long long chunks = (rows + PR_ROWS - 1) / PR_ROWS;
-        const int ctas = (int)std::max<long long>(1, std::min<long long>((chunks + 7) / 8, (long long)ctx->sm_count * 8));
-        {
-            bs_launch_scope sc(ctx, "pearson");
-            k_pearson<<<ctas, PCM_THREADS, sizeof(unsigned long long) * 5 * nslots, ctx->stream>>>(a, nslots);
-        }
-        BS_CUDA(ctx, cudaGetLastError());
-        BS_CUDA(ctx, cudaMemcpyAsync(hsums, dsmall + off_sums, sizeof(unsigned long long) * 5 * nslots, cudaMemcpyDeviceToHost, ctx->stream));
-    }
-    BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     for (auto& c : cands) {
         if (c.slot < 0) continue;
-        if (dtype == BS_DTYPE_F32) c.r = pearson_from_dbl_sums((const double*)hsums + 5 * c.slot, c.npx);
+        if (pd.dtype == BS_DTYPE_F32) c.r = pearson_from_dbl_sums((const double*)hsums + 5 * c.slot, c.npx);
         else c.r = pearson_from_int_sums(hsums + 5 * c.slot, c.npx);
     }
     // Collections.sort(peaks, reverseOrder(by crossCorr, then nPixel)) -- stable
@@ -1732,13 +1877,13 @@ static int pcm_run(bs_ctx* ctx, const void* d1, const void* d2, const long long 
     out->found = 1;
     out->r = best.r;
     out->n_overlap_px = best.npx;
-    const long long li = peaks[best.peak].idx;
+    const long long li = sel->idx[best.peak];
     out->peak_index[0] = li % g.P[0];
     out->peak_index[1] = (li / g.P[0]) % g.P[1];
     out->peak_index[2] = li / ((long long)g.P[0] * g.P[1]);
-    out->pcm_value = peaks[best.peak].val;
+    out->pcm_value = sel->val[best.peak];
     double sub[3] = {0, 0, 0};
-    if (p->do_subpixel) subpixel_offset((const float*)(hsmall + off_nb) + 27 * best.peak, sub);
+    if (pd.p.do_subpixel) subpixel_offset(sel->nb + 27 * best.peak, sub);
     for (int d = 0; d < 3; ++d) {
         out->shift_int[d] = best.shift[d];
         out->shift_sub[d] = (double)best.shift[d] + sub[d];
@@ -1811,11 +1956,25 @@ int bs_pcm_batch(bs_ctx* ctx, int n, const void* const* img1, const void* const*
         const int rc = pcm_geometry(ctx, dims + 3 * i, params->extension, &g);
         if (rc) return rc;
     }
+    // pair i's host half (result read-back, candidate sort, sub-pixel solve) runs after pair i+1 was enqueued.
+    // A change of geometry rebuilds tables / workspace, so the previous pair is finished first.
+    auto same_dims = [&](int i, int j) {
+        return dims[3 * i] == dims[3 * j] && dims[3 * i + 1] == dims[3 * j + 1] && dims[3 * i + 2] == dims[3 * j + 2];
+    };
     if (on_device) {
+        int pending = -1;
         for (int i = 0; i < n; ++i) {
-            int rc = pcm_run(ctx, img1[i], img2[i], dims + 3 * i, dtype, params, out + i);
+            if (pending >= 0 && !same_dims(i, pending)) {
+                int rc = pcm_finish(ctx, pending & 1, out + pending);
+                if (rc) return rc;
+                pending = -1;
+            }
+            int rc = pcm_enqueue(ctx, img1[i], img2[i], dims + 3 * i, dtype, params, i & 1);
             if (rc) return rc;
+            if (pending >= 0 && (rc = pcm_finish(ctx, pending & 1, out + pending))) return rc;
+            pending = i;
         }
+        if (pending >= 0) return pcm_finish(ctx, pending & 1, out + pending);
         return BS_OK;
     }
     // host inputs: double-buffered H2D on the copy stream, overlapped with the previous pair
@@ -1834,14 +1993,22 @@ int bs_pcm_batch(bs_ctx* ctx, int n, const void* const* img1, const void* const*
         return BS_OK;
     };
     if (n > 0 && (rc = enqueue_copy(0))) return rc;
+    int pending = -1;
     for (int i = 0; i < n; ++i) {
         const int b = i & 1;
         if (i + 1 < n && (rc = enqueue_copy(i + 1))) return rc;
+        if (pending >= 0 && !same_dims(i, pending)) {
+            if ((rc = pcm_finish(ctx, pending & 1, out + pending))) return rc;
+            pending = -1;
+        }
         BS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ws.crop_ready[b], 0));
-        rc = pcm_run(ctx, ws.crop[b][0], ws.crop[b][1], dims + 3 * i, dtype, params, out + i);
+        rc = pcm_enqueue(ctx, ws.crop[b][0], ws.crop[b][1], dims + 3 * i, dtype, params, b);
         if (rc) return rc;
         BS_CUDA(ctx, cudaEventRecord(ws.crop_free[b], ctx->stream));
+        if (pending >= 0 && (rc = pcm_finish(ctx, pending & 1, out + pending))) return rc;
+        pending = i;
     }
+    if (pending >= 0) return pcm_finish(ctx, pending & 1, out + pending);
     return BS_OK;
 }
 
