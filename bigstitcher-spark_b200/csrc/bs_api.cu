@@ -47,9 +47,16 @@ void bs_profile_drain(bs_ctx* ctx) {
     ctx->prof_pending.clear();
 }
 
+int bs_volume_acquire(bs_ctx* ctx, bs_volume& v) {
+    if (v.ready_waited) return BS_OK;
+    BS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, v.ready, 0));
+    v.ready_waited = true;
+    return BS_OK;
+}
+
 extern "C" {
 
-int bs_version(void) { return 100; }
+int bs_version(void) { return 101; }
 
 int bs_init(bs_ctx** out, int device, void* stream) {
     if (!out) return bs_set_error(nullptr, BS_ERR_ARG, "bs_init: out is NULL");
@@ -106,6 +113,12 @@ void bs_destroy(bs_ctx* ctx) {
     for (auto& kv : ctx->vols) {
         if (kv.second.owned && kv.second.dev) cudaFree(kv.second.dev);
         if (kv.second.tmaps_dev) cudaFree(kv.second.tmaps_dev);
+        if (kv.second.ready) cudaEventDestroy(kv.second.ready);
+    }
+    for (auto& kv : ctx->vol_pool) {
+        cudaFree(kv.second.dev);
+        if (kv.second.tmaps_dev) cudaFree(kv.second.tmaps_dev);
+        if (kv.second.last_use) cudaEventDestroy(kv.second.last_use);
     }
     bs_pcm_workspace_free(ctx);
     bs_fuse2_free(ctx);
@@ -209,6 +222,58 @@ int bs_volume_upload(bs_ctx* ctx, const void* host, const long long dims[3], int
     return BS_OK;
 }
 
+int bs_volume_upload_async(bs_ctx* ctx, const void* host, const long long dims[3], int dtype,
+                           unsigned long long* handle) {
+    if (!ctx) return BS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!host || !dims || !handle) return bs_set_error(ctx, BS_ERR_ARG, "bs_volume_upload_async: NULL argument");
+    size_t es = dtype_size(dtype);
+    if (!es || dims[0] <= 0 || dims[1] <= 0 || dims[2] <= 0 || dims[0] > 0x7fffffffLL || dims[1] > 0x7fffffffLL ||
+        dims[2] > 0x7fffffffLL)
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_volume_upload_async: bad dtype/dims");
+    BS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)dims[0] * dims[1] * dims[2] * es;
+    bs_volume v;
+    auto it = ctx->vol_pool.find(bytes);
+    if (it != ctx->vol_pool.end()) {
+        bs_pool_entry pe = it->second;
+        ctx->vol_pool.erase(it);
+        v.dev = pe.dev;
+        if (pe.last_use) {
+            // kernels of the buffer's previous life must be done before the copy overwrites it
+            BS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, pe.last_use, 0));
+            cudaEventDestroy(pe.last_use);
+        }
+        if (pe.tmaps_dev) {
+            if (pe.dims[0] == dims[0] && pe.dims[1] == dims[1] && pe.dims[2] == dims[2] && pe.dtype == dtype) {
+                v.tmaps_dev = pe.tmaps_dev;
+                v.tma_state = 1;
+            } else {
+                BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                cudaFree(pe.tmaps_dev);
+            }
+        }
+    } else {
+        BS_CUDA(ctx, cudaMalloc(&v.dev, bytes));
+    }
+    cudaError_t e = cudaMemcpyAsync(v.dev, host, bytes, cudaMemcpyHostToDevice, ctx->copy_stream);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&v.ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(v.ready, ctx->copy_stream);
+    if (e != cudaSuccess) {
+        cudaFree(v.dev);
+        return bs_set_error(ctx, BS_ERR_CUDA, "bs_volume_upload_async: %s", cudaGetErrorString(e));
+    }
+    v.ready_waited = false;
+    v.dims[0] = dims[0]; v.dims[1] = dims[1]; v.dims[2] = dims[2];
+    v.dtype = dtype;
+    v.owned = true;
+    v.pooled = true;
+    v.pool_bytes = bytes;
+    *handle = ctx->next_handle++;
+    ctx->vols[*handle] = v;
+    return BS_OK;
+}
+
 int bs_volume_wrap(bs_ctx* ctx, const void* dev, const long long dims[3], int dtype,
                    unsigned long long* handle) {
     if (!ctx) return BS_ERR_ARG;
@@ -232,12 +297,28 @@ int bs_volume_free(bs_ctx* ctx, unsigned long long handle) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     auto it = ctx->vols.find(handle);
     if (it == ctx->vols.end()) return bs_set_error(ctx, BS_ERR_ARG, "bs_volume_free: unknown handle %llu", handle);
-    if (it->second.owned || it->second.tmaps_dev) {
-        BS_CUDA(ctx, cudaSetDevice(ctx->device));
+    bs_volume& v = it->second;
+    BS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (v.pooled) {
+        // no host synchronisation: the buffer (and its tensor maps, which stay valid for it) goes back to the
+        // pool together with an event that marks the end of everything queued on it so far
+        cudaEvent_t last = nullptr;
+        BS_CUDA(ctx, cudaEventCreateWithFlags(&last, cudaEventDisableTiming));
+        if (!v.ready_waited) BS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, v.ready, 0));
+        BS_CUDA(ctx, cudaEventRecord(last, ctx->stream));
+        bs_pool_entry pe;
+        pe.dev = v.dev;
+        pe.last_use = last;
+        pe.tmaps_dev = v.tmaps_dev;
+        pe.dims[0] = v.dims[0]; pe.dims[1] = v.dims[1]; pe.dims[2] = v.dims[2];
+        pe.dtype = v.dtype;
+        ctx->vol_pool.insert({v.pool_bytes, pe});
+    } else if (v.owned || v.tmaps_dev) {
         BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (it->second.owned) BS_CUDA(ctx, cudaFree(it->second.dev));
-        if (it->second.tmaps_dev) BS_CUDA(ctx, cudaFree(it->second.tmaps_dev));
+        if (v.owned) BS_CUDA(ctx, cudaFree(v.dev));
+        if (v.tmaps_dev) BS_CUDA(ctx, cudaFree(v.tmaps_dev));
     }
+    if (v.ready) cudaEventDestroy(v.ready);
     ctx->vols.erase(it);
     return BS_OK;
 }
@@ -257,9 +338,10 @@ int bs_volume_download(bs_ctx* ctx, unsigned long long handle, void* host) {
     auto it = ctx->vols.find(handle);
     if (it == ctx->vols.end() || !host)
         return bs_set_error(ctx, BS_ERR_ARG, "bs_volume_download: unknown handle or NULL host");
-    const bs_volume& v = it->second;
+    bs_volume& v = it->second;
     size_t bytes = (size_t)v.dims[0] * v.dims[1] * v.dims[2] * dtype_size(v.dtype);
     BS_CUDA(ctx, cudaSetDevice(ctx->device));
+    { int rc = bs_volume_acquire(ctx, v); if (rc) return rc; }
     BS_CUDA(ctx, cudaMemcpyAsync(host, v.dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BS_OK;

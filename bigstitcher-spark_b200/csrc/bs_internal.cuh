@@ -16,8 +16,20 @@ struct bs_volume {
     long long dims[3] = {0, 0, 0};
     int dtype = 0;
     bool owned = false;
+    cudaEvent_t ready = nullptr;  // async upload: H2D copy finished (waited for on the compute stream at first use)
+    bool ready_waited = true;
+    bool pooled = false;          // device buffer comes from / returns to the context's pool
+    size_t pool_bytes = 0;
     void* tmaps_dev = nullptr;   // device copies of the volume's TMA tensor maps (fuse_tma.cu), lazily built
     int tma_state = 0;           // 0 not tried, 1 available, -1 not eligible (dtype / alignment / pitch)
+};
+
+struct bs_pool_entry {
+    void* dev = nullptr;
+    cudaEvent_t last_use = nullptr;   // end of everything that was queued on the buffer in its previous life
+    void* tmaps_dev = nullptr;        // tensor maps stay valid while address, dims and dtype are unchanged
+    long long dims[3] = {0, 0, 0};
+    int dtype = 0;
 };
 
 struct bs_prof_entry {
@@ -73,6 +85,8 @@ struct bs_ctx {
     void* fuse_out = nullptr;         // device staging for host outputs
     size_t fuse_out_cap = 0;
     void* fuse2 = nullptr;            // fuse_tma.cu workspace (Fuse2Ws)
+    // recycled device buffers of async-uploaded volumes, keyed by byte size
+    std::multimap<size_t, bs_pool_entry> vol_pool;
     int sm_count = 148;
     bool pcm_attr_done = false;       // cudaFuncSetAttribute(max dynamic smem) done on this device
 };
@@ -115,6 +129,8 @@ void bs_profile_drain(bs_ctx* ctx);
 // device-buffer helper: (re)allocate when too small
 int bs_ensure_dev(bs_ctx* ctx, void** p, size_t* cap, size_t need);
 
+// make the compute stream wait for a volume's pending async upload (no-op afterwards)
+int bs_volume_acquire(bs_ctx* ctx, bs_volume& v);
 // pcm.cu
 void bs_pcm_workspace_free(bs_ctx* ctx);
 // fuse_tma.cu

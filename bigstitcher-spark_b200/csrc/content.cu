@@ -164,8 +164,9 @@ extern "C" int bs_content_weights(bs_ctx* ctx, unsigned long long vol_handle, do
         return bs_set_error(ctx, BS_ERR_ARG, "bs_content_weights: bad argument");
     auto it = ctx->vols.find(vol_handle);
     if (it == ctx->vols.end()) return bs_set_error(ctx, BS_ERR_ARG, "bs_content_weights: unknown handle %llu", vol_handle);
-    const bs_volume src = it->second;
     BS_CUDA(ctx, cudaSetDevice(ctx->device));
+    { int rc0 = bs_volume_acquire(ctx, it->second); if (rc0) return rc0; }
+    const bs_volume src = it->second;
     BS_CUDA(ctx, cudaFuncSetAttribute((const void*)k_gauss_x, cudaFuncAttributeMaxDynamicSharedMemorySize, GA_SMEM_MAX));
     BS_CUDA(ctx, cudaFuncSetAttribute((const void*)k_gauss_strided, cudaFuncAttributeMaxDynamicSharedMemorySize, GA_SMEM_MAX));
     const long long n = src.dims[0] * src.dims[1] * src.dims[2];
@@ -267,6 +268,7 @@ extern "C" int bs_downsample(bs_ctx* ctx, unsigned long long vol_handle, const i
         if (factors[d] != 1 && factors[d] != 2) return bs_set_error(ctx, BS_ERR_ARG, "bs_downsample: factors must be 1 or 2");
     auto it = ctx->vols.find(vol_handle);
     if (it == ctx->vols.end()) return bs_set_error(ctx, BS_ERR_ARG, "bs_downsample: unknown handle %llu", vol_handle);
+    { int rc0 = bs_volume_acquire(ctx, it->second); if (rc0) return rc0; }
     const bs_volume src = it->second;
     bs_volume v;
     for (int d = 0; d < 3; ++d) {

@@ -566,7 +566,11 @@ static int fuse_prepare(bs_ctx* ctx, const bs_view* views, int n_views, const lo
         auto it = ctx->vols.find(views[i].vol_handle);
         if (it == ctx->vols.end())
             return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: view %d has unknown vol_handle %llu", i, views[i].vol_handle);
-        const bs_volume& vol = it->second;
+        bs_volume& vol = it->second;
+        { int rc = bs_volume_acquire(ctx, vol); if (rc) return rc; }
+        if (views[i].full_dims[0] > 0)
+            return bs_set_error(ctx, BS_ERR_UNSUPPORTED, "bs_fuse: windowed views need uint16 sources with x size a multiple of 8, "
+                                                            "n-linear interpolation and AVG / AVG_BLEND fusion");
         FuseViewDev& d = hv[i];
         if (!bs_invert34(views[i].src_to_world, d.inv))
             return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: view %d has a singular transform", i);

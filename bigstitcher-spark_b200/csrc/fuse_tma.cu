@@ -57,9 +57,11 @@ struct __align__(64) ViewDev {
     const void* data;
     const CUtensorMap* tm_t;      // device copies of the tensor maps (translation box / general box)
     const CUtensorMap* tm_g;
-    int dims[3];
+    int dims[3];                  // size of the (full) view: inside test, blending
     int pad0;
     float border[3], range[3];
+    int wdims[3];                 // resident window [woff, woff + wdims) of the view (== dims, 0 when not windowed)
+    int woff[3];
 };
 
 struct __align__(16) ViewItem {   // per (tile, view); 112 B
@@ -72,9 +74,11 @@ struct __align__(16) ViewItem {   // per (tile, view); 112 B
         float m[9];               // general: linear part of world -> source
     };
     float dm1[3], border[3], inv_range[3];
+    int tma[3];                   // box origin in WINDOW coordinates, x a multiple of 8 (the TMA coordinates)
+    int ox;                       // translation: column of the tile's first tap inside the box (0..7)
     int pad[1];
 };
-static_assert(sizeof(ViewItem) == 112, "ViewItem layout");
+static_assert(sizeof(ViewItem) == 128, "ViewItem layout");
 constexpr int VI_WORDS = sizeof(ViewItem) / 4;
 
 struct TileHdr { int first, count, mode, pad; };   // mode 0: no view, 1: resident (TMA), 2: gather from global
@@ -153,7 +157,7 @@ __device__ __forceinline__ CullOut cull_view(const ViewDev& v, int vi, const dou
                                              bool use_blend, ViewItem* it) {
     CullOut r{true, true};
     int flags = VI_INSIDE | VI_PLAT_X | VI_PLAT_Y | VI_PLAT_Z;
-    int b0[3];
+    int b0[3], tma[3] = {0, 0, 0}, ox = 0;
     float o[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
@@ -167,6 +171,8 @@ __device__ __forceinline__ CullOut cull_view(const ViewDev& v, int vi, const dou
             const double b = w0[a] + ft;           // exact integer
             b0[a] = (int)b;
             o[a] = (float)(t - ft);
+            tma[a] = b0[a] - v.woff[a];
+            if (a == 0) { ox = tma[0] & 7; tma[0] &= ~7; }   // 16-byte aligned TMA box origin
             lo = b + (t - ft);
             hi = lo + ext[a];
         } else {
@@ -175,7 +181,8 @@ __device__ __forceinline__ CullOut cull_view(const ViewDev& v, int vi, const dou
             hi = org + fmax(0.0, m0 * ext[0]) + fmax(0.0, m1 * ext[1]) + fmax(0.0, m2 * ext[2]);
             const double eps = 2e-3 + 2e-7 * fmax(fabs(lo), fabs(hi));
             int f0 = max((int)floor(fmax(lo - eps, 0.0)), 0);
-            if (a == 0) f0 &= ~7;                      // 16-byte aligned TMA box origin
+            if (a == 0) f0 = v.woff[0] + ((f0 - v.woff[0]) & ~7);   // 16-byte aligned TMA box origin (window coordinates)
+            tma[a] = f0 - v.woff[a];
             const int f1 = min((int)floor(fmin(hi + eps, dm1)), dim - 1) + 1;
             const int cap = a == 0 ? BXG : (a == 1 ? BYG : BZG);
             if (f1 - f0 + 1 > cap) r.fits = false;
@@ -200,6 +207,7 @@ __device__ __forceinline__ CullOut cull_view(const ViewDev& v, int vi, const dou
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         it->b0[a] = b0[a];
+        it->tma[a] = tma[a];
         it->o[a] = o[a];
         it->dm1[a] = (float)(v.dims[a] - 1);
         it->border[a] = v.border[a];
@@ -219,6 +227,7 @@ __device__ __forceinline__ CullOut cull_view(const ViewDev& v, int vi, const dou
             it->m[3 * a + 2] = (float)v.inv[4 * a + 2];
         }
     }
+    it->ox = ox;
     it->pad[0] = 0;
     return r;
 }
@@ -379,7 +388,7 @@ __device__ __forceinline__ void tr_tile(const FuseArgs2& a, const unsigned char*
     for (int v = 0; v < C; ++v) {
         const int s = (T.it0 + v) % NST_T;
         const ViewItem& d = descs[s];
-        const int ox = d.b0[0] & 7;            // column of the tile's first tap inside the 8-aligned box
+        const int ox = d.ox;                   // column of the tile's first tap inside the 8-aligned box
         base[v] = reinterpret_cast<const unsigned int*>(slots + (size_t)s * SLOT_T) + (2 * ly) * (BXT / 2) + lx + (ox >> 1);
         sel01[v] = (ox & 1) ? 0x5432u : 0x3210u;
         sel2[v] = (ox & 1) ? 0x7632u : 0x7610u;
@@ -436,7 +445,7 @@ template <typename T>
 __device__ __forceinline__ float gather8(const T* __restrict__ d, int dx, int dy, int dz, float sx, float sy, float sz) {
     const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
     const float rx = sx - fx, ry = sy - fy, rz = sz - fz;
-    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const int x0 = min(max((int)fx, 0), dx - 1), y0 = min(max((int)fy, 0), dy - 1), z0 = min(max((int)fz, 0), dz - 1);
     const int x1 = min(x0 + 1, dx - 1), y1 = min(y0 + 1, dy - 1), z1 = min(z0 + 1, dz - 1);
     const size_t r00 = ((size_t)z0 * dy + y0) * dx, r01 = ((size_t)z0 * dy + y1) * dx;
     const size_t r10 = ((size_t)z1 * dy + y0) * dx, r11 = ((size_t)z1 * dy + y1) * dx;
@@ -472,7 +481,7 @@ __device__ __forceinline__ void tr_tile_many(const FuseArgs2& a, const unsigned 
             const ViewItem& d = descs[s];
             const float wk = d.wz[k];
             if (wk == 0.f) continue;   // team-uniform
-            const int ox = d.b0[0] & 7;
+            const int ox = d.ox;
             const unsigned int sel01 = (ox & 1) ? 0x5432u : 0x3210u, sel2 = (ox & 1) ? 0x7632u : 0x7610u;
             const unsigned int* base = reinterpret_cast<const unsigned int*>(slots + (size_t)s * SLOT_T) +
                                        (k * BYT + 2 * ly) * (BXT / 2) + lx + (ox >> 1);
@@ -523,7 +532,8 @@ __device__ __forceinline__ void tr_slow_tile(const FuseArgs2& a, const TileRec& 
                 const float w = (blend_factor(sx, d.dm1[0], d.border[0], d.inv_range[0], ub) *
                                  blend_factor(sy, d.dm1[1], d.border[1], d.inv_range[1], ub)) * d.wz[k];
                 if (!(w > 0.f)) continue;
-                const float val = gather8((const unsigned short*)V.data, V.dims[0], V.dims[1], V.dims[2], sx, sy, sz);
+                const float val = gather8((const unsigned short*)V.data, V.wdims[0], V.wdims[1], V.wdims[2],
+                                          sx - (float)V.woff[0], sy - (float)V.woff[1], sz - (float)V.woff[2]);
                 swi = swi + w * val;
                 sw = sw + w;
             }
@@ -558,9 +568,11 @@ __device__ __forceinline__ void gen_tile(const FuseArgs2& a, const unsigned char
             const bool plateau = (flags & (VI_PLAT_X | VI_PLAT_Y | VI_PLAT_Z)) == (VI_PLAT_X | VI_PLAT_Y | VI_PLAT_Z);
             const void* gdata = nullptr;
             int gdx = 0, gdy = 0, gdz = 0;
+            float gox = 0.f, goy = 0.f, goz = 0.f;
             if (!resident) {
                 const ViewDev& V = a.views[d.view];
-                gdata = V.data; gdx = V.dims[0]; gdy = V.dims[1]; gdz = V.dims[2];
+                gdata = V.data; gdx = V.wdims[0]; gdy = V.wdims[1]; gdz = V.wdims[2];
+                gox = (float)V.woff[0]; goy = (float)V.woff[1]; goz = (float)V.woff[2];
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -600,7 +612,7 @@ __device__ __forceinline__ void gen_tile(const FuseArgs2& a, const unsigned char
                     val = c0 + tz * (c1 - c0);
                 } else {
                     val = 0.f;
-                    if (ok) val = gather8((const unsigned short*)gdata, gdx, gdy, gdz, rx + b0x, ry + b0y, rz + b0z);
+                    if (ok) val = gather8((const unsigned short*)gdata, gdx, gdy, gdz, rx + b0x - gox, ry + b0y - goy, rz + b0z - goz);
                 }
                 if (ok) {
                     swi[q] = swi[q] + w * val;
@@ -717,7 +729,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fuse_tma_kernel(const __grid_cons
                                 if (d.view < 64) fenced |= 1ull << d.view;
                             }
                             mbar_expect_tx(&full[s], (GENERAL ? BXG * BYG * BZG : BXT * BYT * BZT) * 2);
-                            tma_load_box(slots + (size_t)s * SLOT, tm, d.b0[0] & ~7, d.b0[1], d.b0[2], &full[s]);
+                            tma_load_box(slots + (size_t)s * SLOT, tm, d.tma[0], d.tma[1], d.tma[2], &full[s]);
                         }
                     }
                 }
@@ -895,7 +907,8 @@ int fuse2_launch(bs_ctx* ctx, const bs_view* views, int n_views, int nb, const l
     std::vector<ViewDev> hv((size_t)n_views);
     bool general = false;
     for (int i = 0; i < n_views; ++i) {
-        const bs_volume& vol = ctx->vols.find(views[i].vol_handle)->second;
+        bs_volume& vol = ctx->vols.find(views[i].vol_handle)->second;
+        { int rc = bs_volume_acquire(ctx, vol); if (rc) return rc; }
         ViewDev& d = hv[i];
         memset(&d, 0, sizeof(d));
         if (!bs_invert34(views[i].src_to_world, d.inv))
@@ -907,8 +920,15 @@ int fuse2_launch(bs_ctx* ctx, const bs_view* views, int n_views, int nb, const l
         d.data = vol.dev;
         d.tm_t = (const CUtensorMap*)vol.tmaps_dev;
         d.tm_g = (const CUtensorMap*)vol.tmaps_dev + 1;
+        const bool windowed = views[i].full_dims[0] > 0;
         for (int k = 0; k < 3; ++k) {
-            d.dims[k] = (int)vol.dims[k];
+            d.wdims[k] = (int)vol.dims[k];
+            d.woff[k] = windowed ? (int)views[i].window_min[k] : 0;
+            d.dims[k] = windowed ? (int)views[i].full_dims[k] : (int)vol.dims[k];
+            if (windowed && (views[i].window_min[k] < 0 || views[i].window_min[k] + vol.dims[k] > views[i].full_dims[k] ||
+                             views[i].full_dims[k] > 0x7fffffffLL))
+                return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: view %d: window [%lld, +%lld) outside full_dims %lld", i,
+                                    views[i].window_min[k], vol.dims[k], views[i].full_dims[k]);
             d.border[k] = views[i].blend_border[k];
             d.range[k] = views[i].blend_range[k];
         }
@@ -917,7 +937,7 @@ int fuse2_launch(bs_ctx* ctx, const bs_view* views, int n_views, int nb, const l
         for (int r = 0; r < 3; ++r) {
             double lo = f[4 * r + 3], hi = f[4 * r + 3], mag = 0.0;
             for (int c = 0; c < 3; ++c) {
-                const double e = f[4 * r + c] * (double)(vol.dims[c] - 1);
+                const double e = f[4 * r + c] * (double)(d.dims[c] - 1);
                 lo += std::min(0.0, e);
                 hi += std::max(0.0, e);
                 mag += std::fabs(f[4 * r + c]);

@@ -701,6 +701,67 @@ __global__ void __launch_bounds__(PCM_THREADS, 2) k_fft_strided_pipe(const __gri
     }
 }
 
+// Persistent, software-pipelined cross-power pass (z): same three tile buffers as k_fft_strided mode 1 (so two
+// CTAs still fit an SM), but the loads are cp.async groups that overlap the transforms:
+//   A(t) lands -> FFT A   | B(t) still in flight
+//   B(t) lands -> FFT B -> normalise, conj(A) * B
+//   B's buffer is free    -> prefetch A(t+1) under the transform of the product
+//   the transform's scratch buffer is free -> prefetch B(t+1) under the store and FFT A(t+1)
+template <class F>
+__global__ void __launch_bounds__(PCM_THREADS, 2) k_fft_xpower_pipe(const __grid_constant__ StridedPipeArgs p) {
+    const StridedArgs& a = p.s;
+    const int tshift = F::kStatic ? F::LSHIFT : a.tshift;
+    const int TW = 1 << tshift, N = F::kStatic ? F::N : a.plan.n;
+    const int twpad = (N + 1) & ~1;
+    float2* tw = bs_sm;
+    float2* bufA = bs_sm + twpad;
+    float2* bufB = bufA + (size_t)N * TW;
+    float2* pong = bufB + (size_t)N * TW;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = a.tw[i];
+    const int vshift = tshift - 1, vmask = (1 << vshift) - 1, nvec = N << vshift;
+    auto tile_off = [&](int t) -> size_t {
+        const int tx = t % p.tiles_x, o = t / p.tiles_x;
+        return (size_t)o * a.ostride + (size_t)tx * TW;
+    };
+    auto prefetch = [&](const float2* g, float2* dst) {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = threadIdx.x; i < nvec; i += blockDim.x)
+            cp_async16(d4 + i, reinterpret_cast<const float4*>(g + (long long)(i >> vshift) * a.estride) + (i & vmask));
+        cp_async_commit();
+    };
+    int t = blockIdx.x;
+    if (t < p.n_tiles) {
+        prefetch(a.a + tile_off(t), bufA);
+        prefetch(a.b + tile_off(t), bufB);
+    }
+    for (; t < p.n_tiles; t += gridDim.x) {
+        const int tn = t + gridDim.x;
+        const bool has_next = tn < p.n_tiles;
+        cp_async_wait<1>();            // A(t) landed (B(t) is the newest group)
+        __syncthreads();
+        float2* rA = F::run(bufA, pong, tw, a.plan, tshift, TW, 1);
+        float2* freeA = (rA == bufA) ? pong : bufA;
+        cp_async_wait<0>();            // B(t) landed
+        __syncthreads();
+        float2* rB = F::run(bufB, freeA, tw, a.plan, tshift, TW, 1);
+        float2* free2 = (rB == bufB) ? freeA : bufB;
+        const int tot = N * TW;
+        for (int i = threadIdx.x; i < tot; i += blockDim.x) {
+            const float2 x = unit_or_zero(rA[i], a.thresh);
+            const float2 y = unit_or_zero(rB[i], a.thresh);
+            rA[i] = make_float2(x.x * y.x + x.y * y.y, x.x * y.y - x.y * y.x);  // conj(x) * y
+        }
+        __syncthreads();
+        if (has_next) prefetch(a.a + tile_off(tn), rB);          // rB's buffer is free from here on
+        float2* rQ = F::run(rA, free2, tw, a.plan, tshift, TW, 1);
+        float2* otherQ = (rQ == rA) ? free2 : rA;
+        if (has_next) prefetch(a.b + tile_off(tn), otherQ);      // scratch of the last transform is free
+        tile_store(a.a + tile_off(t), rQ, a.estride, N, tshift);
+        __syncthreads();               // rQ is read out: it becomes the next iteration's scratch
+        bufA = rB; bufB = otherQ; pong = rQ;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // x pass, complex -> real, in place
 
@@ -1468,6 +1529,9 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         if ((rc = set_smem(ctx, (const void*)k_fft_strided_pipe<FftS540>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_strided_pipe<FftS540R2>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_strided_pipe<FftGeneric>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_xpower_pipe<FftS540R2>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_xpower_pipe<FftS540>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_xpower_pipe<FftGeneric>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftX270>, 0))) return rc;
         ctx->pcm_attr_done = true;
     }
@@ -1567,7 +1631,18 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         a.thresh = 1e-5f;  // PhaseCorrelation2Util.normalizeInterval threshold
         dim3 grid(g.pitch >> g.tshift_z, g.P[1], 1);
         bs_launch_scope sc(ctx, "fft_z_xpower");
-        if (g.static_z && g.tshift_z == 3 && env_int("BS_FFT_Z_R2", 1)) k_fft_strided<FftS540R2><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
+        if (env_int("BS_FFT_Z_PIPE", 1) && g.tshift_z >= 1 && !(g.static_z && g.tshift_z == 2)) {
+            StridedPipeArgs pp;
+            pp.s = a;
+            pp.tiles_x = g.pitch >> g.tshift_z;
+            pp.n_other = g.P[1];
+            pp.n_tiles = pp.tiles_x * pp.n_other;
+            const int per_sm = std::max(1, std::min(2, (int)(PCM_SMEM_MAX / (g.smem_z + 1024))));
+            const int nctas = std::min(pp.n_tiles, ctx->sm_count * per_sm);
+            if (g.static_z && g.tshift_z == 3 && env_int("BS_FFT_Z_R2", 1)) k_fft_xpower_pipe<FftS540R2><<<nctas, PCM_THREADS, g.smem_z, ctx->stream>>>(pp);
+            else if (g.static_z && g.tshift_z == 3) k_fft_xpower_pipe<FftS540><<<nctas, PCM_THREADS, g.smem_z, ctx->stream>>>(pp);
+            else k_fft_xpower_pipe<FftGeneric><<<nctas, PCM_THREADS, g.smem_z, ctx->stream>>>(pp);
+        } else if (g.static_z && g.tshift_z == 3 && env_int("BS_FFT_Z_R2", 1)) k_fft_strided<FftS540R2><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
         else if (g.static_z && g.tshift_z == 2) k_fft_strided<FftS540T4><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
         else if (g.static_z) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
         else k_fft_strided<FftGeneric><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
@@ -2005,6 +2080,85 @@ int bs_pcm_batch(bs_ctx* ctx, int n, const void* const* img1, const void* const*
         rc = pcm_enqueue(ctx, ws.crop[b][0], ws.crop[b][1], dims + 3 * i, dtype, params, b);
         if (rc) return rc;
         BS_CUDA(ctx, cudaEventRecord(ws.crop_free[b], ctx->stream));
+        if (pending >= 0 && (rc = pcm_finish(ctx, pending & 1, out + pending))) return rc;
+        pending = i;
+    }
+    if (pending >= 0) return pcm_finish(ctx, pending & 1, out + pending);
+    return BS_OK;
+}
+
+int bs_pcm_volumes_batch(bs_ctx* ctx, int n, const bs_pcm_job* jobs, const bs_pcm_params* params, bs_pcm_result* out) {
+    if (!ctx) return BS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n < 0 || (n > 0 && (!jobs || !params || !out))) return bs_set_error(ctx, BS_ERR_ARG, "bs_pcm_volumes_batch: NULL argument");
+    if (n == 0) return BS_OK;
+    BS_CUDA(ctx, cudaSetDevice(ctx->device));
+    // validate everything before any launch
+    size_t maxb = 0;
+    bool need_crop = false;
+    int dtype = -1;
+    for (int i = 0; i < n; ++i) {
+        const bs_pcm_job& j = jobs[i];
+        auto i1 = ctx->vols.find(j.vol1), i2 = ctx->vols.find(j.vol2);
+        if (i1 == ctx->vols.end() || i2 == ctx->vols.end())
+            return bs_set_error(ctx, BS_ERR_ARG, "bs_pcm_volumes_batch: job %d has an unknown volume handle", i);
+        if (i1->second.dtype != i2->second.dtype) return bs_set_error(ctx, BS_ERR_ARG, "bs_pcm_volumes_batch: job %d mixes dtypes", i);
+        if (dtype >= 0 && i1->second.dtype != dtype) return bs_set_error(ctx, BS_ERR_ARG, "bs_pcm_volumes_batch: mixed dtypes in one batch");
+        dtype = i1->second.dtype;
+        for (int d = 0; d < 3; ++d) {
+            if (j.dims[d] <= 0 || j.min1[d] < 0 || j.min2[d] < 0 || j.min1[d] + j.dims[d] > i1->second.dims[d] ||
+                j.min2[d] + j.dims[d] > i2->second.dims[d])
+                return bs_set_error(ctx, BS_ERR_ARG, "bs_pcm_volumes_batch: job %d: overlap interval outside the volume (axis %d)", i, d);
+        }
+        PcmGeometry g;
+        int rc = pcm_geometry(ctx, j.dims, params->extension, &g);
+        if (rc) return rc;
+        const bool whole1 = j.dims[0] == i1->second.dims[0] && j.dims[1] == i1->second.dims[1] && j.dims[2] == i1->second.dims[2];
+        const bool whole2 = j.dims[0] == i2->second.dims[0] && j.dims[1] == i2->second.dims[1] && j.dims[2] == i2->second.dims[2];
+        if (!whole1 || !whole2) {
+            need_crop = true;
+            maxb = std::max(maxb, crop_bytes_of(j.dims, dtype));
+        }
+    }
+    int rc = pcm_check_params(ctx, params, dtype);
+    if (rc) return rc;
+    if (need_crop && (rc = ensure_crop_buffers(ctx, maxb, 2))) return rc;
+    bs_pcm_workspace& ws = ctx->ws;
+    const size_t es = dtype == BS_DTYPE_U16 ? 2 : dtype == BS_DTYPE_F32 ? 4 : 1;
+    // the overlap crop of a volume: the volume itself when the interval covers it, else a strided device copy
+    auto crop = [&](bs_volume& v, const long long mn[3], const long long dims[3], void* dst, const void** out_ptr) -> int {
+        if (dims[0] == v.dims[0] && dims[1] == v.dims[1] && dims[2] == v.dims[2]) { *out_ptr = v.dev; return BS_OK; }
+        cudaMemcpy3DParms p;
+        memset(&p, 0, sizeof(p));
+        p.srcPtr = make_cudaPitchedPtr(v.dev, (size_t)v.dims[0] * es, (size_t)v.dims[0], (size_t)v.dims[1]);
+        p.srcPos = make_cudaPos((size_t)mn[0] * es, (size_t)mn[1], (size_t)mn[2]);
+        p.dstPtr = make_cudaPitchedPtr(dst, (size_t)dims[0] * es, (size_t)dims[0], (size_t)dims[1]);
+        p.extent = make_cudaExtent((size_t)dims[0] * es, (size_t)dims[1], (size_t)dims[2]);
+        p.kind = cudaMemcpyDeviceToDevice;
+        BS_CUDA(ctx, cudaMemcpy3DAsync(&p, ctx->stream));
+        ctx->launches++;
+        *out_ptr = dst;
+        return BS_OK;
+    };
+    auto same_dims = [&](int i, int j) {
+        return jobs[i].dims[0] == jobs[j].dims[0] && jobs[i].dims[1] == jobs[j].dims[1] && jobs[i].dims[2] == jobs[j].dims[2];
+    };
+    int pending = -1;
+    for (int i = 0; i < n; ++i) {
+        const bs_pcm_job& j = jobs[i];
+        bs_volume& v1 = ctx->vols.find(j.vol1)->second;
+        bs_volume& v2 = ctx->vols.find(j.vol2)->second;
+        if ((rc = bs_volume_acquire(ctx, v1)) || (rc = bs_volume_acquire(ctx, v2))) return rc;
+        if (pending >= 0 && !same_dims(i, pending)) {
+            if ((rc = pcm_finish(ctx, pending & 1, out + pending))) return rc;
+            pending = -1;
+        }
+        const int b = i & 1;
+        const void *p1 = nullptr, *p2 = nullptr;
+        // crop buffers of slot b were last read by pair i-2's Pearson kernel: same stream, already ordered
+        if ((rc = crop(v1, j.min1, j.dims, need_crop ? ws.crop[b][0] : nullptr, &p1))) return rc;
+        if ((rc = crop(v2, j.min2, j.dims, need_crop ? ws.crop[b][1] : nullptr, &p2))) return rc;
+        if ((rc = pcm_enqueue(ctx, p1, p2, j.dims, dtype, params, b))) return rc;
         if (pending >= 0 && (rc = pcm_finish(ctx, pending & 1, out + pending))) return rc;
         pending = i;
     }

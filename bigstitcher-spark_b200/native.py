@@ -51,7 +51,12 @@ class PcmResultC(C.Structure):
 class ViewC(C.Structure):
     _fields_ = [("src_to_world", C.c_double * 12), ("vol_handle", C.c_ulonglong),
                 ("content_handle", C.c_ulonglong), ("blend_border", C.c_float * 3),
-                ("blend_range", C.c_float * 3)]
+                ("blend_range", C.c_float * 3), ("full_dims", C.c_longlong * 3), ("window_min", C.c_longlong * 3)]
+
+
+class PcmJobC(C.Structure):
+    _fields_ = [("vol1", C.c_ulonglong), ("vol2", C.c_ulonglong), ("min1", C.c_longlong * 3),
+                ("min2", C.c_longlong * 3), ("dims", C.c_longlong * 3)]
 
 
 class FuseParamsC(C.Structure):
@@ -79,8 +84,8 @@ _lib = None
 SYMBOLS = [
     "bs_version", "bs_init", "bs_destroy", "bs_last_error", "bs_synchronize", "bs_launch_count",
     "bs_profile_enable", "bs_profile_reset", "bs_profile_get", "bs_host_alloc", "bs_host_free",
-    "bs_pcm_default_params", "bs_pcm_pair", "bs_pcm_batch", "bs_good_fft_size", "bs_pcm_debug_pcm",
-    "bs_fuse_default_params", "bs_volume_upload", "bs_volume_wrap", "bs_volume_free",
+    "bs_pcm_default_params", "bs_pcm_pair", "bs_pcm_batch", "bs_pcm_volumes_batch", "bs_good_fft_size", "bs_pcm_debug_pcm",
+    "bs_fuse_default_params", "bs_volume_upload", "bs_volume_upload_async", "bs_volume_wrap", "bs_volume_free",
     "bs_content_weights", "bs_volume_download", "bs_volume_devptr", "bs_downsample", "bs_fuse_block", "bs_fuse_blocks",
     "bs_fuse_block_to_volume", "bs_fuse_accumulate", "bs_fuse_finish",
 ]
@@ -121,6 +126,8 @@ def load_library():
     lib.bs_fuse_default_params.argtypes = [P(FuseParamsC)]
     lib.bs_fuse_default_params.restype = None
     lib.bs_volume_upload.argtypes = [vp, vp, P(ll), ip, P(ull)]
+    lib.bs_volume_upload_async.argtypes = [vp, vp, P(ll), ip, P(ull)]
+    lib.bs_pcm_volumes_batch.argtypes = [vp, ip, P(PcmJobC), P(PcmParams), P(PcmResultC)]
     lib.bs_volume_wrap.argtypes = [vp, vp, P(ll), ip, P(ull)]
     lib.bs_volume_free.argtypes = [vp, ull]
     lib.bs_content_weights.argtypes = [vp, ull, dbl, dbl, P(ull)]
@@ -272,6 +279,21 @@ class Context:
                                           1 if on_dev else 0, out))
         return [self._result(out[i]) for i in range(n)]
 
+    def pcm_volumes_batch(self, jobs, params: PcmParams | None = None):
+        """jobs: iterable of (vol1, vol2, min1_xyz, min2_xyz, dims_xyz) on resident volumes; the overlap crops are
+        cut on the device (a tile is uploaded once and reused by all its pairs)."""
+        jobs = list(jobs)
+        params = params or self.pcm_params()
+        arr = (PcmJobC * max(1, len(jobs)))()
+        for i, (v1, v2, m1, m2, d) in enumerate(jobs):
+            arr[i].vol1, arr[i].vol2 = int(v1), int(v2)
+            arr[i].min1[:] = [int(x) for x in m1]
+            arr[i].min2[:] = [int(x) for x in m2]
+            arr[i].dims[:] = [int(x) for x in d]
+        out = (PcmResultC * max(1, len(jobs)))()
+        self._check(self.lib.bs_pcm_volumes_batch(self.h, len(jobs), arr, C.byref(params), out))
+        return [self._result(out[i]) for i in range(len(jobs))]
+
     def pcm_debug_pcm(self, img1: np.ndarray, img2: np.ndarray, extension=(10, 10, 10)) -> np.ndarray:
         dims = (C.c_longlong * 3)(*img1.shape[::-1])
         ext = (C.c_int * 3)(*extension)
@@ -290,6 +312,17 @@ class Context:
         h = C.c_ulonglong()
         vol = np.ascontiguousarray(vol)
         self._check(self.lib.bs_volume_upload(self.h, vol.ctypes.data, dims, _NP2BS[vol.dtype], C.byref(h)))
+        return h.value
+
+    def volume_upload_async(self, vol) -> int:
+        """Queue the H2D copy of a PINNED host array (numpy view of a pinned buffer / pinned torch tensor) on the
+        copy stream; later calls using the handle wait for it on the device.  The array must stay alive."""
+        p, on_dev, _ = _ptr_of(vol)
+        if on_dev:
+            raise ValueError("volume_upload_async needs a host buffer")
+        dims = (C.c_longlong * 3)(*tuple(vol.shape)[::-1])
+        h = C.c_ulonglong()
+        self._check(self.lib.bs_volume_upload_async(self.h, p, dims, _bs_dtype(vol), C.byref(h)))
         return h.value
 
     def volume_wrap(self, dev_ptr, dims_xyz, dtype) -> int:
@@ -347,6 +380,8 @@ class Context:
             arr[i].content_handle = int(v.get("content_handle", 0))
             arr[i].blend_border[:] = [float(x) for x in v.get("blend_border", (0, 0, 0))]
             arr[i].blend_range[:] = [float(x) for x in v.get("blend_range", (40, 40, 40))]
+            arr[i].full_dims[:] = [int(x) for x in v.get("full_dims", (0, 0, 0))]
+            arr[i].window_min[:] = [int(x) for x in v.get("window_min", (0, 0, 0))]
         return arr, len(views)
 
     def fuse_block(self, views, block_min_xyz, block_size_xyz, params: FuseParamsC | None = None, out=None):

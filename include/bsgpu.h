@@ -113,6 +113,16 @@ int bs_pcm_batch(bs_ctx* ctx, int n, const void* const* img1, const void* const*
                  const long long* dims /* n*3 */, int dtype, const bs_pcm_params* params,
                  int on_device, bs_pcm_result* out /* n */);
 
+/* Pairs given as resident volumes plus the raster overlap intervals PairwiseStitching.getShift derives from the
+ * two translations (BigStitcher 2.5.0; call site J/SparkPairwiseStitching.java:247-255): a tile is uploaded ONCE
+ * (bs_volume_upload[_async]) and takes part in up to 26 pairs; the overlap crops are cut on the device. */
+typedef struct {
+    unsigned long long vol1, vol2;   /* resident volumes (same dtype) */
+    long long min1[3], min2[3];      /* first voxel of the overlap in each volume's own pixel coordinates */
+    long long dims[3];               /* overlap size (equal for both; getShift returns null otherwise) */
+} bs_pcm_job;
+int bs_pcm_volumes_batch(bs_ctx* ctx, int n, const bs_pcm_job* jobs, const bs_pcm_params* params, bs_pcm_result* out);
+
 /* padded FFT length policy of this build (smallest 2^a3^b5^c >= n; even when even != 0) */
 int bs_good_fft_size(int n, int even);
 
@@ -131,6 +141,14 @@ typedef struct {
     unsigned long long content_handle;   /* content-weight volume (bs_content_weights) or 0 */
     float              blend_border[3];  /* source px, after FusionTools.adjustBlending */
     float              blend_range[3];
+    /* Windowed source (block-wise staging, J/fusion/OverlappingBlocks.java:133-161 / J/util/ViewUtil.java:210-371:
+     * only the source cells a block touches are loaded): when full_dims[0] > 0 the resident volume holds the
+     * sub-interval [window_min, window_min + volume dims) of a view whose real size is full_dims; src_to_world
+     * still maps FULL-view pixel coordinates, the inside test and the blending weights use full_dims, taps are
+     * fetched relative to window_min.  The caller guarantees the window covers every tap with non-zero weight
+     * (taps outside read zero).  All zeros = the volume is the whole view. */
+    long long          full_dims[3];
+    long long          window_min[3];
 } bs_view;
 
 typedef struct {
@@ -146,6 +164,12 @@ void bs_fuse_default_params(bs_fuse_params* p);
 
 int bs_volume_upload(bs_ctx* ctx, const void* host, const long long dims[3], int dtype,
                      unsigned long long* handle);
+/* same, but asynchronous: `host` must be pinned (bs_host_alloc) and stay valid until the copy has run; the copy is
+ * queued on the context's copy stream and every later call that uses the handle waits for it on the device, so
+ * tile uploads overlap the kernels of earlier work (no host synchronisation).  Device buffers of volumes created
+ * this way are recycled through a per-context pool by bs_volume_free. */
+int bs_volume_upload_async(bs_ctx* ctx, const void* host, const long long dims[3], int dtype,
+                           unsigned long long* handle);
 /* register device memory owned by the caller (not freed by bs_volume_free) */
 int bs_volume_wrap(bs_ctx* ctx, const void* dev, const long long dims[3], int dtype,
                    unsigned long long* handle);

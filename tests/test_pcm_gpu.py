@@ -199,3 +199,40 @@ def test_full_512_pair_subpixel_bench_unit(ctx):
     pg = ctx.pcm_debug_pcm(a, b)
     pc = po.calculate_pcm(a, b, workers=-1)
     assert np.abs(pg - pc).max() < 2e-4 * np.abs(pc).max()
+
+
+def _pinned(arr):
+    import torch
+    t = torch.from_numpy(arr.view(np.int16) if arr.dtype == np.uint16 else arr).pin_memory()
+    return t, (t.numpy().view(np.uint16) if arr.dtype == np.uint16 else t.numpy())
+
+
+def test_volumes_batch_crops_on_device(ctx):
+    """Tiles are uploaded once (async, pinned) and every pair's overlap crop is cut on the device:
+    bit-identical to running the host-cropped pair."""
+    G = synth.field((96, 120, 200), seed=101, sigma=1.5)
+    tA = synth.tile_from(G, (8, 10, 12), (64, 72, 96), 1)
+    tB = synth.tile_from(G, (8 + 2, 10 - 3, 12 + 70), (64, 72, 96), 2)     # true offset of B in A's frame: (70, -3, 2)
+    keep = [_pinned(tA), _pinned(tB)]
+    hA, hB = ctx.volume_upload_async(keep[0][1]), ctx.volume_upload_async(keep[1][1])
+    # nominal registration says B starts at x = 66: overlap = A[66:96] x B[0:30] (x), full y / z
+    jobs = [(hA, hB, (66, 0, 0), (0, 0, 0), (30, 72, 64)),
+            (hA, hA, (0, 0, 0), (0, 0, 0), (96, 72, 64)),          # whole volumes: no crop copy
+            (hB, hA, (0, 0, 0), (66, 0, 0), (30, 72, 64))]
+    got = ctx.pcm_volumes_batch(jobs)
+    a, b = np.ascontiguousarray(tA[:, :, 66:96]), np.ascontiguousarray(tB[:, :, 0:30])
+    assert got[0] == ctx.pcm_pair(a, b)
+    o = po.pcm_shift(a, b)
+    assert got[0].found and got[0].shift_int == o.shift_int and abs(got[0].r - o.r) < 1e-9
+    assert got[0].shift_int == (-4, 3, -2)      # planted: B's content sits 4 px further right than the nominal 66
+    assert got[1].shift_int == (0, 0, 0) and abs(got[1].r - 1.0) < 1e-12
+    assert got[2] == ctx.pcm_pair(b, a)
+    ctx.volume_free(hA)
+    ctx.volume_free(hB)
+    # recycled pool buffer: a second upload of the same size reuses the device allocation
+    hC = ctx.volume_upload_async(keep[0][1])
+    assert ctx.pcm_volumes_batch([(hC, hC, (0, 0, 0), (0, 0, 0), (96, 72, 64))])[0].shift_int == (0, 0, 0)
+    ctx.volume_free(hC)
+    import bsgpu
+    with pytest.raises(bsgpu.BsError):
+        ctx.pcm_volumes_batch([(12345, 12345, (0, 0, 0), (0, 0, 0), (8, 8, 8))])
