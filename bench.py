@@ -238,8 +238,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": nsteps, "steps_requested": args.steps, "warmup": 1, "ms_per_step": 1000.0 * procs / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"phase-correlation: bounded sample of the {n}^3 uint16 overlap-crop workload "
-                               f"(BASELINE configs[1]), 5-smooth pad, peaks=5, subpixel, minOverlap 0.25",
+        "config": {"workload": WORKLOAD_PCM if n == 512 else f"phase-correlation: {n}^3 uint16 overlap crops",
+                   "sampling": f"every step is a bounded sample of that workload: {procs} concurrent pairs",
                    "note": "Java reference not runnable in this image (no JVM; arithmetic in un-vendored Maven "
                            "artefacts); CPU arm = numpy/scipy-pocketfft oracle port on the host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs * threads, "host_cores": ncores,
@@ -251,11 +251,24 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+WORKLOAD_PCM = ("phase-correlation: 112 overlapping pairs of 512^3 uint16 overlap crops (BASELINE configs[1], 4x4x2 tile "
+                "grid), 5-smooth pad 540^3, peaks=5, subpixel, minOverlap 0.25")
+
+
+def ncu_traffic_r2(tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the committed `ncu --set full` capture of the
+    CURRENT kernels (profiles/ncu_traffic_r2.json; bench.py cannot run ncu itself), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r2.json")
+    try:
+        return json.load(open(p))[tag]
+    except Exception:
+        return None
+
+
 def run_gpu(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import bsgpu
-    from bsgpu import fusion as bfusion
     from bsgpu import synthetic
 
     # ---- CPU baseline first (rank 0, N=1): forks worker processes, so it runs before CUDA is touched
@@ -318,10 +331,27 @@ def run_gpu(args, rank, world, local_rank):
     res = None
     for _ in range(max(args.warmup, 3)):
         res = step_resident()
-    recovered = sum(1 for r, s in zip(res, shifts) if r.found and tuple(r.shift_int) == tuple(s))
+    # planted real-valued shifts (half of the pairs carry a Fourier-domain sub-pixel part)
+    recovered = sum(1 for r, s in zip(res, shifts) if r.found and max(abs(a - b) for a, b in zip(r.shift_sub, s)) < 0.3)
+    sub_err = [max(abs(a - b) for a, b in zip(r.shift_sub, s)) for r, s in zip(res, shifts) if r.found]
     P = res[0].pad
     pearson_px_mean = float(np.mean([r.pearson_px for r in res]))
     ncand_mean = float(np.mean([r.n_candidates for r in res]))
+
+    # ---- parity spot check against the oracle, outside the timed region (rank 0, N = 1): one integer-shift pair
+    # and one sub-pixel pair of the benchmarked workload
+    oracle_check = None
+    if rank == 0 and world == 1 and not args.skip_oracle:
+        from oracle import pcm_oracle as po
+        ok = []
+        for i in (0, 1)[:min(2, npairs)]:
+            a = imgs1[i].cpu().numpy().view(np.uint16)
+            b = imgs2[i].cpu().numpy().view(np.uint16)
+            o = po.pcm_shift(a, b, workers=-1)
+            g = res[i]
+            ok.append(bool(g.found == o.found and g.shift_int == o.shift_int and g.peak_index == o.peak_index and
+                           abs(g.r - o.r) < 1e-9 and max(abs(x - y) for x, y in zip(g.shift_sub, o.shift_sub)) < 1e-3))
+        oracle_check = f"{sum(ok)}/{len(ok)} pairs identical to oracle/pcm_oracle.py (index, shift, r 1e-9, sub-pixel 1e-3)"
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -331,23 +361,6 @@ def run_gpu(args, rank, world, local_rank):
     clocks = sampler.stop()
     ms_per_step = ms / args.steps
     value = world * npairs / (ms_per_step / 1000.0)
-
-    # ---- e2e: same C-ABI call, pinned host buffers, H2D inside the timed region
-    nh = min(args.host_pairs, npairs)
-    h1 = [imgs1[i].cpu().pin_memory() for i in range(nh)]
-    h2 = [imgs2[i].cpu().pin_memory() for i in range(nh)]
-    hn1 = [h1[i % nh].numpy().view(np.uint16) for i in range(npairs)]
-    hn2 = [h2[i % nh].numpy().view(np.uint16) for i in range(npairs)]
-
-    def step_host():
-        return ctx.pcm_batch(hn1, hn2, params)
-
-    rh = step_host()
-    assert all(a.shift_int == b.shift_int for a, b in zip(rh[:nh], res[:nh]))
-    e2e_ms, _ = timed(step_host, args.steps)
-    e2e_value = world * npairs / (e2e_ms / args.steps / 1000.0)
-    h2d_bytes = npairs * 2 * n ** 3 * 2
-    d2h_bytes = npairs * 128  # one bs_pcm_result per pair (+ peak lists, < 100 KB per pair)
 
     # ---- per-kernel device timing (CUDA events on the launching stream, separate pass)
     kern = {}
@@ -365,15 +378,55 @@ def run_gpu(args, rank, world, local_rank):
                 avg = tms / cnt
                 kern[tag] = {"ms": round(avg, 4), "alg_bytes": int(b), "gbs": round(b / avg / 1e6, 1),
                              "frac": round(b / avg / 1e6 / peak_gbs, 4)}
-    del hn1, hn2, h1, h2
+    del imgs1, imgs2
+    torch.cuda.empty_cache()
+
+    # ---- e2e: the `stitching` command's shape.  The 32 tiles of the 4x4x2 grid are uploaded ONCE per step from
+    # pinned host memory (async, on the copy stream) and the 112 pairs are phase-correlated on the resident tiles
+    # (crops cut on the device; here the overlap crop is the whole 512^3 tile, the unit north_star names)
+    e2e = None
+    if not args.skip_pcm_e2e:
+        ntile = 32
+        tiles, offs = synthetic.make_pcm_grid_workload(n=n, device=dev, seed=43 + rank, n_tiles=ntile)
+        host_tiles = [t.cpu().pin_memory() for t in tiles]
+        host_np = [h.numpy().view(np.uint16) for h in host_tiles]
+        del tiles
+        torch.cuda.empty_cache()
+        gpairs = synthetic.grid_pairs_4x4x2()
+        gpairs = sorted(gpairs, key=lambda p: max(p))          # pairs become runnable as their tiles arrive
+        if npairs < len(gpairs):
+            gpairs = gpairs[:npairs]
+        used = sorted({t for p in gpairs for t in p})
+
+        def step_host():
+            hs = {t: ctx.volume_upload_async(host_np[t]) for t in used}
+            jobs = [(hs[a], hs[b], (0, 0, 0), (0, 0, 0), (n, n, n)) for a, b in gpairs]
+            out = ctx.pcm_volumes_batch(jobs, params)
+            for h in hs.values():
+                ctx.volume_free(h)
+            return out
+
+        rh = step_host()
+        good = 0
+        for (a, b), r in zip(gpairs, rh):
+            want = tuple(offs[b][d] - offs[a][d] for d in range(3))     # img2(p) = img1(p + s), s = s_b - s_a
+            good += int(r.found and tuple(r.shift_int) == want)
+        step_host()
+        e2e_ms, _ = timed(step_host, args.steps)
+        e2e_value = world * len(gpairs) / (e2e_ms / args.steps / 1000.0)
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": len(used) * n ** 3 * 2,
+               "d2h_bytes_per_step": len(gpairs) * 2400, "ms_per_step": e2e_ms / args.steps,
+               "what": f"{len(used)} tiles of {n}^3 uint16 uploaded once per step from pinned host memory "
+                       f"(bs_volume_upload_async), {len(gpairs)} pairs on the resident tiles (bs_pcm_volumes_batch), "
+                       f"one result block read back per pair",
+               "recovered_planted_shifts": f"{good}/{len(gpairs)}"}
+        del host_np, host_tiles
 
     # ---------------------------------------------------------------- affine fusion (config 3)
     fusion_obj = None
     if not args.skip_fusion:
-        del imgs1, imgs2
         torch.cuda.empty_cache()
         fusion_obj = bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
-
     if fusion_obj is not None and cpu_fusion is not None:
         fusion_obj["cpu_baseline"] = cpu_fusion
 
@@ -382,9 +435,11 @@ def run_gpu(args, rank, world, local_rank):
         dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
         roof = None
         if dom:
+            tr = ncu_traffic_r2("pcm") or {}
             roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["gbs"], "peak": peak_gbs, "unit": "GB/s",
-                    "frac": kern[dom]["frac"], "traffic": ncu_traffic(dom) if (n, tuple(P)) == (512, (540, 540, 540)) else None,
-                    "traffic_source": "profiles/ncu_traffic_r1.json (ncu --set full capture of the same kernel, 512^3 pair)",
+                    "frac": kern[dom]["frac"],
+                    "traffic": tr.get(dom) if (n, tuple(P)) == (512, (540, 540, 540)) else None,
+                    "traffic_source": "profiles/ncu_traffic_r2.json (ncu --set full capture of this round's kernels, 512^3 pair)",
                     "peak_source": peak_src,
                     "alg_bytes_per_launch": kern[dom]["alg_bytes"], "ms_per_launch": kern[dom]["ms"],
                     "kernels": kern,
@@ -395,13 +450,16 @@ def run_gpu(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"phase-correlation: {npairs} pairs/GPU of {n}^3 uint16 overlap crops "
-                                   f"(BASELINE configs[1]), pad {P[0]}x{P[1]}x{P[2]}, peaks=5, subpixel, minOverlap 0.25",
+            "config": {"workload": WORKLOAD_PCM if (npairs, n) == (112, 512) else
+                       f"phase-correlation: {npairs} pairs/GPU of {n}^3 uint16 overlap crops, pad {P[0]}x{P[1]}x{P[2]}",
                        "pairs_per_gpu": npairs, "l2": "inputs larger than L2 (no flush needed)",
-                       "distinct_fields": args.fields, "recovered_planted_shifts": f"{recovered}/{npairs}",
-                       "mean_pearson_candidates": ncand_mean, "e2e_distinct_host_pairs": nh},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                    "ms_per_step": e2e_ms / args.steps},
+                       "distinct_fields": args.fields,
+                       "planted_shifts": "integer in [-20,20]^3, every second pair + Fourier-domain sub-pixel part in [-0.5,0.5)^3",
+                       "recovered_planted_shifts": f"{recovered}/{npairs} within 0.3 px",
+                       "max_subpixel_error_px": round(float(max(sub_err)), 4) if sub_err else None,
+                       "oracle_check": oracle_check,
+                       "mean_pearson_candidates": ncand_mean},
+            "e2e": e2e,
             "gpu_launches": int(launches), "wall_ms_timed": wall_ms, "clocks": clocks,
             "roofline": roof, "cpu_baseline": cpu, "fusion": fusion_obj,
         }
@@ -418,6 +476,7 @@ def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
     import bsgpu
     from bsgpu import fusion as bf
     from bsgpu import synthetic
+    nat = bsgpu.native
 
     g, tile, stride, out_n = args.fusion_grid, args.fusion_tile, args.fusion_stride, args.fusion_size
     tiles, models, tdims = synthetic.make_fusion_workload((g, g, g), tile, stride, dev, n_distinct=args.fusion_distinct)
@@ -428,95 +487,71 @@ def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
     zs = out_n // world
     z_lo, z_hi = rank * zs, (rank + 1) * zs if rank < world - 1 else out_n
     mine = bf.find_overlapping_views(vdims, regs, (0, 0, z_lo), (out_n - 1, out_n - 1, z_hi - 1))
-    handles = {i: ctx.volume_wrap(tiles[i], tdims, bsgpu.native.DTYPE_U16) for i in mine}
+    handles = {i: ctx.volume_wrap(tiles[i], tdims, nat.DTYPE_U16) for i in mine}
     blending = {i: bf.adjust_blending(models[i]) for i in mine}
     grid = [b for b in bf.grid_create((out_n, out_n, out_n), (256, 256, 128), (128, 128, 128))
             if z_lo <= b[0][2] < z_hi]
-    out = torch.empty(sum(int(np.prod(b[1])) for b in grid), dtype=torch.float32, device=dev)
-    params = ctx.fuse_params("AVG_BLEND", 1, bsgpu.native.DTYPE_F32)
-    jobs = []
-    jobs_e2e = []
-    off = 0
-    for (o, s, _) in grid:
-        vids = bf.find_overlapping_views(vdims, regs, o, tuple(o[d] + s[d] - 1 for d in range(3)), mine)
-        jobs_e2e.append((vids, o, s))
-        views = ctx.make_views(dict(src_to_world=models[v], vol_handle=handles[v], blend_border=blending[v][0],
-                                    blend_range=blending[v][1]) for v in vids)
-        jobs.append((views, o, s, out.data_ptr() + 4 * off))
-        off += int(np.prod(s))
-    nvox_rank = off
+    grid.sort(key=lambda b: (b[0][2], b[0][1], b[0][0]))
+    nvox_rank = sum(int(np.prod(b[1])) for b in grid)
     nvox_total = out_n ** 3
+    out = torch.empty(nvox_rank, dtype=torch.float32, device=dev)
+    CH = args.fusion_blocks_per_call
 
-    def step_resident():
-        for views, o, s, p in jobs:
-            ctx.fuse_block(views, o, s, params, out=p)
+    def build_calls(view_dicts, out_ptr, esize):
+        """one bs_fuse_blocks call per CH super-blocks (the work-queue form of the reference's per-block tasks)"""
+        calls, off = [], 0
+        for c0 in range(0, len(grid), CH):
+            chunk = grid[c0:c0 + CH]
+            lo = tuple(min(b[0][d] for b in chunk) for d in range(3))
+            hi = tuple(max(b[0][d] + b[1][d] - 1 for b in chunk) for d in range(3))
+            vids = bf.find_overlapping_views(vdims, regs, lo, hi, mine)
+            views = ctx.make_views(view_dicts[v] for v in vids)
+            ptrs = []
+            for (_, sz, _g) in chunk:
+                ptrs.append(out_ptr + esize * off)
+                off += int(np.prod(sz))
+            calls.append((views, [b[0] for b in chunk], [b[1] for b in chunk], ptrs, vids))
+        return calls
 
-    for _ in range(3):
-        step_resident()
-    l0 = ctx.launch_count()
-    ms, _ = timed(step_resident, args.steps)
-    launches = ctx.launch_count() - l0
-    ms_step = ms / args.steps
+    def view_dict(v, handle):
+        return dict(src_to_world=models[v], vol_handle=handle, blend_border=blending[v][0], blend_range=blending[v][1])
+
+    def run_variant(fusion_type, view_dicts, steps):
+        p = ctx.fuse_params(fusion_type, 1, nat.DTYPE_F32)
+        calls = build_calls(view_dicts, out.data_ptr(), 4)
+
+        def step():
+            for views, mins, sizes, ptrs, _ in calls:
+                ctx.fuse_blocks(views, mins, sizes, p, outs=ptrs)
+        for _ in range(3):
+            step()
+        l0 = ctx.launch_count()
+        ms, _ = timed(step, steps)
+        return ms / steps, ctx.launch_count() - l0, step
+
+    vd = {v: view_dict(v, handles[v]) for v in mine}
+    ms_step, launches, step_resident = run_variant("AVG_BLEND", vd, args.steps)
+    launches //= args.steps
     value = nvox_total / (ms_step / 1000.0) / 1e6
 
-    # e2e: tiles uploaded from pinned host memory and every block read back to the host
-    hosts = {}
-    for i in mine:
-        key = tiles[i].data_ptr()
-        if key not in hosts and not args.skip_fusion_e2e:
-            hosts[key] = tiles[i].cpu().pin_memory()
-    # e2e: the host design the C ABI is meant for -- a work queue drained by worker threads, each with
-    # its own bs_ctx on the same device (ctypes drops the GIL inside the calls), so one worker's
-    # D2H of a finished block overlaps the other's kernel; tiles are uploaded once and shared by
-    # bs_volume_devptr + bs_volume_wrap.
-    import threading
-    NWORK = 2
-    wctx = [ctx] + [bsgpu.Context(dev.index) for _ in range(NWORK - 1)]
-    houts = [torch.empty(256 * 256 * 128, dtype=torch.float32).pin_memory().numpy() for _ in range(NWORK)]
+    # ---- parity spot check against the C oracle, outside the timed region: one super-block at a 8-tile junction
+    oracle_check = None
+    if rank == 0 and world == 1 and not args.skip_oracle and (g, tile, stride) == (4, 576, 491):
+        try:
+            from oracle import c_fusion, fusion_oracle as fo
+            bmin, bsz = (384, 384, 384), (256, 256, 128)
+            vids = bf.find_overlapping_views(vdims, regs, bmin, tuple(bmin[d] + bsz[d] - 1 for d in range(3)), mine)
+            ov = [fo.View(tiles[v].cpu().numpy().view(np.uint16), models[v], blending[v][0], blending[v][1], None) for v in vids]
+            want = c_fusion.fuse_block(ov, bmin, bsz, fo.AVG_BLEND)
+            got = ctx.fuse_block(ctx.make_views(vd[v] for v in vids), bmin, bsz, ctx.fuse_params("AVG_BLEND", 1, nat.DTYPE_F32))
+            err = np.abs(got - want) / np.maximum(np.abs(want), 250.0)
+            oracle_check = (f"super-block {bmin}+{bsz}, {len(vids)} views: max rel err {float(err.max()):.2e}, "
+                            f"{int((err > 1e-4).sum())} of {err.size} voxels beyond 1e-4 (oracle/c/fusion_oracle.c)")
+            del ov, want, got
+        except Exception as e:  # the check must never take the bench down
+            oracle_check = f"failed: {e}"
 
-    def step_host():
-        hs = {}
-        lock = threading.Lock()
-
-        def upload(w):
-            for i in mine[w::NWORK]:
-                h = wctx[w].volume_upload(hosts[tiles[i].data_ptr()].numpy().view(np.uint16))
-                with lock:
-                    hs[i] = (w, h)
-        th = [threading.Thread(target=upload, args=(w,)) for w in range(NWORK)]
-        [t.start() for t in th]
-        [t.join() for t in th]
-        # every worker context gets a handle for every tile
-        wh = [dict() for _ in range(NWORK)]
-        for i, (w0, h) in hs.items():
-            ptr = wctx[w0].volume_devptr(h)
-            for w in range(NWORK):
-                wh[w][i] = h if w == w0 else wctx[w].volume_wrap(ptr, tdims, bsgpu.native.DTYPE_U16)
-
-        def fuse(w):
-            for (vids, o, s) in jobs_e2e[w::NWORK]:
-                views = wctx[w].make_views(dict(src_to_world=models[v], vol_handle=wh[w][v], blend_border=blending[v][0],
-                                                blend_range=blending[v][1]) for v in vids)
-                wctx[w].fuse_block(views, o, s, params, out=houts[w][:int(np.prod(s))].reshape(s[2], s[1], s[0]))
-        th = [threading.Thread(target=fuse, args=(w,)) for w in range(NWORK)]
-        [t.start() for t in th]
-        [t.join() for t in th]
-        for w in range(NWORK):
-            for i, h in wh[w].items():
-                wctx[w].volume_free(h)
-
-    rev = {handles[i]: i for i in mine}
-    if args.skip_fusion_e2e:
-        e2e_ms_step, e2e_value = float("nan"), float("nan")
-    else:
-        step_host()
-        e2e_ms, _ = timed(step_host, max(1, min(args.steps, 2)))
-        e2e_ms_step = e2e_ms / max(1, min(args.steps, 2))
-        e2e_value = nvox_total / (e2e_ms_step / 1000.0) / 1e6
-    h2d = len(mine) * tile ** 3 * 2
-    d2h = nvox_rank * 4
-
-    # per-kernel timing pass
+    # ---- per-kernel timing pass + roofline of the fusion kernel
     roof = None
     if rank == 0:
         ctx.profile_reset()
@@ -524,6 +559,7 @@ def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
         step_resident()
         ctx.profile_enable(False)
         tms, cnt = ctx.profile_get("fuse")
+        pms, pcnt = ctx.profile_get("fuse_plan")
         src_vox = 0
         for i in mine:
             bmin, bmax = bf.transformed_bounding_box(tdims, models[i])
@@ -532,26 +568,127 @@ def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
             src_vox += int(np.prod(np.maximum(hi - lo + 1, 0)))
         alg = nvox_rank * 4 + src_vox * 2
         if cnt:
-            roof = {"bound": "hbm", "kernel": "fuse_kernel", "achieved": round(alg / tms / 1e6, 1), "peak": peak_gbs,
-                    "unit": "GB/s", "frac": round(alg / tms / 1e6 / peak_gbs, 4), "traffic": None,
-                    "traffic_note": "the 33.5 MB output of one super-block stays in the 126 MB L2 under ncu replay; "
-                                    "profiles/ncu_r1_summary.md lists the captured DRAM reads",
+            tr = ncu_traffic_r2("fusion") or {}
+            traffic = None
+            if tr.get("bytes_per_voxel"):
+                traffic = int(tr["bytes_per_voxel"] * nvox_rank / cnt)
+            roof = {"bound": "hbm", "kernel": "fuse_tma_kernel<translation>", "achieved": round(alg / tms / 1e6, 1),
+                    "peak": peak_gbs, "unit": "GB/s", "frac": round(alg / tms / 1e6 / peak_gbs, 4), "traffic": traffic,
+                    "traffic_source": "profiles/ncu_traffic_r2.json: dram read+write bytes per output voxel of the ncu --set full "
+                                      "capture (64 super-blocks, 2.1 GB output + 1.8 GB input: larger than L2), scaled to this launch",
                     "peak_source": peak_src, "alg_bytes_per_step": int(alg), "alg_bytes_per_launch": int(alg / cnt),
                     "ms_per_launch": round(tms / cnt, 4), "launches_per_step": int(cnt),
+                    "plan_kernel_ms_per_step": round(pms, 4),
                     "bytes_per_voxel": round(alg / nvox_rank, 3), "kernel_only_mvox_s": round(nvox_rank / tms / 1e3, 1)}
+
+    # ---- named variants (resident): 0.5 degree rotation (general affine kernel), content-based blending
+    variants = {}
+    if not args.skip_fusion_variants:
+        t2, m2, _ = synthetic.make_fusion_workload((g, g, g), tile, stride, dev, n_distinct=args.fusion_distinct, rot_deg=0.5)
+        del t2
+        models_rot = m2
+        vd_rot = {v: dict(src_to_world=models_rot[v], vol_handle=handles[v], blend_border=bf.adjust_blending(models_rot[v])[0],
+                          blend_range=bf.adjust_blending(models_rot[v])[1]) for v in mine}
+        ms_r, _, _ = run_variant("AVG_BLEND", vd_rot, max(1, min(args.steps, 2)))
+        variants["rotated_0.5deg"] = {"value": nvox_total / (ms_r / 1000.0) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_r,
+                                      "kernel": "fuse_tma_kernel<general>"}
+        if not args.skip_fusion_content:
+            # content-based weights G_s2 * (I - G_s1 * I)^2 (sigma 20 / 40) are precomputed per DISTINCT tile volume
+            t0 = time.perf_counter()
+            chandle = {}
+            for v in mine:
+                key = tiles[v].data_ptr()
+                if key not in chandle:
+                    chandle[key] = ctx.content_weights(handles[v], 20.0, 40.0)
+            ctx.synchronize()
+            pre_s = time.perf_counter() - t0
+            vd_c = {v: dict(vd[v], content_handle=chandle[tiles[v].data_ptr()]) for v in mine}
+            ms_c, _, _ = run_variant("AVG_BLEND_CONTENT", vd_c, 1)
+            variants["content_based"] = {"value": nvox_total / (ms_c / 1000.0) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_c,
+                                         "fusion_type": "AVG_BLEND_CONTENT", "sigma": [20.0, 40.0],
+                                         "alg_bytes_per_voxel": 12.54, "kernel": "fuse_kernel (generic tile kernel)",
+                                         "content_precompute_s": round(pre_s, 3),
+                                         "content_volumes": len(chandle)}
+            for h in chandle.values():
+                ctx.volume_free(h)
+
+    # ---- e2e: the `affine-fusion` command's shape.  Every step uploads the z-range of each tile that the rank's
+    # slab needs from pinned host memory (windowed views, async on the copy stream), fuses CH super-blocks per call
+    # and streams the blocks back to pinned host buffers on the D2H stream while the next group is fused.
+    e2e = None
+    e2e_u16 = None
+    if not args.skip_fusion_e2e:
+        hosts = {}
+        for i in mine:
+            key = tiles[i].data_ptr()
+            if key not in hosts:
+                hosts[key] = tiles[i].cpu().pin_memory()
+        win = {}
+        for i in mine:
+            bmin, bmax = bf.transformed_bounding_box(tdims, models[i])
+            w0 = int(max(0, np.floor(z_lo - models[i][2][3]) - 2))
+            w1 = int(min(tdims[2] - 1, np.ceil(z_hi - 1 - models[i][2][3]) + 2))
+            win[i] = (w0, w1)
+        order = sorted(mine, key=lambda v: models[v][2][3])
+        ring_n = min(len(grid), 2 * CH)
+        ring_f32 = torch.empty((ring_n, 256 * 256 * 128), dtype=torch.float32).pin_memory()
+
+        def make_step(out_dtype, ring):
+            esz = 4 if out_dtype == nat.DTYPE_F32 else 2
+            p = ctx.fuse_params("AVG_BLEND", 1, out_dtype, 0, 0.0, 65535.0)
+            ring_np = ring.numpy()
+
+            def step_host():
+                hs = {}
+                for i in order:
+                    w0, w1 = win[i]
+                    sub = hosts[tiles[i].data_ptr()].numpy().view(np.uint16)[w0:w1 + 1]
+                    hs[i] = ctx.volume_upload_async(sub)
+                vdw = {v: dict(vd[v], vol_handle=hs[v], full_dims=tdims, window_min=(0, 0, win[v][0])) for v in mine}
+                slot = 0
+                for c0 in range(0, len(grid), CH):
+                    chunk = grid[c0:c0 + CH]
+                    lo = tuple(min(b[0][d] for b in chunk) for d in range(3))
+                    hi = tuple(max(b[0][d] + b[1][d] - 1 for b in chunk) for d in range(3))
+                    vids = bf.find_overlapping_views(vdims, regs, lo, hi, mine)
+                    outs = []
+                    for (_, sz, _g) in chunk:
+                        outs.append(ring_np[slot % ring_n][:int(np.prod(sz))].reshape(sz[2], sz[1], sz[0]))
+                        slot += 1
+                    ctx.fuse_blocks(ctx.make_views(vdw[v] for v in vids), [b[0] for b in chunk], [b[1] for b in chunk], p, outs=outs)
+                for h in hs.values():
+                    ctx.volume_free(h)
+            return step_host, esz
+
+        step_host, esz = make_step(nat.DTYPE_F32, ring_f32)
+        step_host()
+        nst = max(1, min(args.steps, 2))
+        e2e_ms, _ = timed(step_host, nst)
+        h2d = sum((win[i][1] - win[i][0] + 1) * tdims[0] * tdims[1] * 2 for i in mine)
+        e2e = {"value": nvox_total / (e2e_ms / nst / 1000.0) / 1e6, "unit": "Mvoxels/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(nvox_rank * 4), "ms_per_step": e2e_ms / nst,
+               "what": "tiles' needed z-ranges uploaded from pinned host memory every step (windowed views, async), "
+                       f"{CH} super-blocks per bs_fuse_blocks call, float32 blocks streamed to pinned host buffers"}
+        del ring_f32
+        ring_u16 = torch.empty((ring_n, 256 * 256 * 128), dtype=torch.int16).pin_memory()
+        step_host16, _ = make_step(nat.DTYPE_U16, ring_u16.view(torch.int16))
+        step_host16()
+        e2e16_ms, _ = timed(step_host16, nst)
+        e2e_u16 = {"value": nvox_total / (e2e16_ms / nst / 1000.0) / 1e6, "unit": "Mvoxels/s", "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(nvox_rank * 2), "ms_per_step": e2e16_ms / nst,
+                   "what": "same with uint16 output (the reference's usual -d UINT16, min 0 / max 65535)"}
+        del ring_u16, hosts
+
     for h in handles.values():
         ctx.volume_free(h)
-    for c in wctx[1:]:
-        c.close()
     return {"metric": "fused Mvoxels/sec (affine fusion, AVG_BLEND, float32 out)", "value": value, "unit": "Mvoxels/s",
             "scaling": "strong", "ms_per_step": ms_step, "gpu_launches": int(launches),
             "config": {"workload": f"{g}x{g}x{g} grid of {tile}^3 uint16 tiles (stride {stride}, jitter +-2 px) -> "
                                    f"{out_n}^3 float32, super-blocks 256x256x128, z-slab per GPU",
                        "distinct_tile_volumes": args.fusion_distinct, "views_on_rank0": len(mine),
-                       "e2e_worker_threads": NWORK,
+                       "blocks_per_call": CH, "oracle_check": oracle_check,
                        "l2": "output 34 GB + inputs larger than L2"},
-            "e2e": {"value": e2e_value, "unit": "Mvoxels/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms_step},
+            "e2e": e2e, "e2e_uint16": e2e_u16, "variants": variants,
             "roofline": roof}
 
 
@@ -564,10 +701,14 @@ def main():
     ap.add_argument("--pairs", type=int, default=112)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--fields", type=int, default=4)
-    ap.add_argument("--host-pairs", type=int, default=8)
     ap.add_argument("--skip-fusion", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-fusion-e2e", action="store_true")
+    ap.add_argument("--skip-pcm-e2e", action="store_true")
+    ap.add_argument("--skip-oracle", action="store_true", help="skip the oracle spot checks outside the timed region")
+    ap.add_argument("--skip-fusion-variants", action="store_true")
+    ap.add_argument("--skip-fusion-content", action="store_true")
+    ap.add_argument("--fusion-blocks-per-call", type=int, default=64)
     ap.add_argument("--skip-pcm", action="store_true", help="debug: tiny PCM workload")
     ap.add_argument("--ref-full", action="store_true", help="reference arm: run all warm-up steps too")
     ap.add_argument("--fusion-grid", type=int, default=4)

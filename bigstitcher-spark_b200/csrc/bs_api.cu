@@ -100,6 +100,13 @@ int bs_init(bs_ctx** out, int device, void* stream) {
         delete ctx;
         return bs_set_error(nullptr, BS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
     }
+    e = cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        cudaStreamDestroy(ctx->copy_stream);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return bs_set_error(nullptr, BS_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
     *out = ctx;
     return BS_OK;
 }
@@ -109,6 +116,7 @@ void bs_destroy(bs_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
+    cudaStreamSynchronize(ctx->d2h_stream);
     bs_profile_drain(ctx);
     for (auto& kv : ctx->vols) {
         if (kv.second.owned && kv.second.dev) cudaFree(kv.second.dev);
@@ -129,6 +137,7 @@ void bs_destroy(bs_ctx* ctx) {
     if (ctx->fuse_out) cudaFree(ctx->fuse_out);
     if (ctx->fuse_plan) cudaFree(ctx->fuse_plan);
     cudaStreamDestroy(ctx->copy_stream);
+    cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -61,7 +61,8 @@ struct bs_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaStream_t copy_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;   // host -> device copies
+    cudaStream_t d2h_stream = nullptr;    // device -> host copies (PCIe is full duplex: never share the H2D stream)
     std::mutex mu;
     std::string err;
     std::unordered_map<unsigned long long, bs_volume> vols;

@@ -1162,7 +1162,7 @@ int bs_fuse_blocks(bs_ctx* ctx, const bs_view* views, int n_views, int n_blocks,
     if (out_on_device) return fuse_blocks_dev(ctx, views, n_views, n_blocks, block_min, block_size, params, outs);
 
     // host destinations: blocks are fused in groups into one of two device staging buffers; the D2H copies of
-    // a group run on the copy stream while the next group is being fused
+    // a group run on the D2H stream while the next group is being fused
     Fuse2Ws* W = ws_of(ctx);
     const size_t es = bs_out_elem_size(params->out_dtype);
     const size_t group_cap = (size_t)256 << 20;
@@ -1188,7 +1188,7 @@ int bs_fuse_blocks(bs_ctx* ctx, const bs_view* views, int n_views, int n_blocks,
         if (used[sb]) BS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, W->stage_done[sb], 0));
         if (W->stage_cap[sb] < bytes) {
             // growing a staging buffer: everything in flight on it must be finished
-            BS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+            BS_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
             rc = bs_ensure_dev(ctx, &W->stage[sb], &W->stage_cap[sb], bytes);
             if (rc) return rc;
         }
@@ -1197,17 +1197,17 @@ int bs_fuse_blocks(bs_ctx* ctx, const bs_view* views, int n_views, int n_blocks,
         rc = fuse_blocks_dev(ctx, views, n_views, b1 - b0, block_min + 3 * b0, block_size + 3 * b0, params, douts.data());
         if (rc) return rc;
         BS_CUDA(ctx, cudaEventRecord(W->stage_ready[sb], ctx->stream));
-        BS_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, W->stage_ready[sb], 0));
+        BS_CUDA(ctx, cudaStreamWaitEvent(ctx->d2h_stream, W->stage_ready[sb], 0));
         for (int b = b0; b < b1; ++b) {
             const size_t nbytes = (size_t)block_size[3 * b] * block_size[3 * b + 1] * block_size[3 * b + 2] * es;
-            BS_CUDA(ctx, cudaMemcpyAsync(outs[b], douts[(size_t)(b - b0)], nbytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            BS_CUDA(ctx, cudaMemcpyAsync(outs[b], douts[(size_t)(b - b0)], nbytes, cudaMemcpyDeviceToHost, ctx->d2h_stream));
         }
-        BS_CUDA(ctx, cudaEventRecord(W->stage_done[sb], ctx->copy_stream));
+        BS_CUDA(ctx, cudaEventRecord(W->stage_done[sb], ctx->d2h_stream));
         used[sb] = true;
         b0 = b1;
         ++g;
     }
-    BS_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    BS_CUDA(ctx, cudaStreamSynchronize(ctx->d2h_stream));
     BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return BS_OK;
 }

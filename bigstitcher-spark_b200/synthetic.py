@@ -48,16 +48,31 @@ def tile_from_field(field, off_zyx, shape_zyx, seed, noise=30.0):
     return torch.clamp(torch.round(t), 0, 32767).to(torch.int16).contiguous()
 
 
-def make_pcm_workload(n_pairs, n=512, device="cuda", seed=42, n_fields=4, max_shift=20):
-    """BASELINE config 2: ``n_pairs`` overlap-crop pairs of n^3 uint16 with planted integer shifts
-    drawn uniformly from [-max_shift, max_shift]^3 (numpy default_rng(seed)).  Returns
-    (imgs1, imgs2, shifts_xyz).  Pair i is cut from field i % n_fields (field seed 2000 + f),
+def fourier_shift(field, shift_zyx):
+    """field translated by a real-valued shift: out(p) = field(p + shift) (periodic), via the Fourier shift theorem."""
+    import torch
+    nz, ny, nx = field.shape
+    F = torch.fft.rfftn(field)
+    kz = torch.fft.fftfreq(nz, device=field.device)[:, None, None]
+    ky = torch.fft.fftfreq(ny, device=field.device)[None, :, None]
+    kx = torch.fft.rfftfreq(nx, device=field.device)[None, None, :]
+    ph = 2.0 * np.pi * (kz * shift_zyx[0] + ky * shift_zyx[1] + kx * shift_zyx[2])
+    F = F * torch.polar(torch.ones_like(ph), ph)
+    return torch.fft.irfftn(F, s=(nz, ny, nx))
+
+
+def make_pcm_workload(n_pairs, n=512, device="cuda", seed=42, n_fields=4, max_shift=20, subpixel_every=2):
+    """BASELINE config 2: ``n_pairs`` overlap-crop pairs of n^3 uint16 with planted integer shifts drawn
+    uniformly from [-max_shift, max_shift]^3 (numpy default_rng(seed)); every ``subpixel_every``-th pair (half of
+    them by default) carries an additional Fourier-domain sub-pixel shift in [-0.5, 0.5)^3.  Returns
+    (imgs1, imgs2, shifts_xyz) with real-valued shifts.  Pair i is cut from field i % n_fields (field seed 2000 + f),
     tile noise seeds 100000 + 2i / 2i + 1."""
     rng = np.random.default_rng(seed)
-    shifts = rng.integers(-max_shift, max_shift + 1, size=(n_pairs, 3))
+    shifts = rng.integers(-max_shift, max_shift + 1, size=(n_pairs, 3)).astype(np.float64)
+    fracs = rng.uniform(-0.5, 0.5, size=(n_pairs, 3))
     m = max_shift + 4
     big = (n + 2 * m,) * 3
-    imgs1, imgs2 = [], []
+    imgs1, imgs2, planted = [], [], []
     fields = {}
     for i in range(n_pairs):
         f = i % n_fields
@@ -65,9 +80,54 @@ def make_pcm_workload(n_pairs, n=512, device="cuda", seed=42, n_fields=4, max_sh
             fields[f] = smooth_field(big, 2000 + f, device)
         sx, sy, sz = (int(v) for v in shifts[i])
         imgs1.append(tile_from_field(fields[f], (m, m, m), (n, n, n), 100000 + 2 * i))
-        imgs2.append(tile_from_field(fields[f], (m + sz, m + sy, m + sx), (n, n, n), 100001 + 2 * i))
+        src = fields[f]
+        total = shifts[i].copy()
+        if subpixel_every and i % subpixel_every == 1:
+            fx, fy, fz = fracs[i]
+            src = fourier_shift(fields[f], (fz, fy, fx))
+            total = total + fracs[i]
+        imgs2.append(tile_from_field(src, (m + sz, m + sy, m + sx), (n, n, n), 100001 + 2 * i))
+        planted.append(tuple(float(v) for v in total))
+        del src
     del fields
-    return imgs1, imgs2, [tuple(int(v) for v in s) for s in shifts]
+    return imgs1, imgs2, planted
+
+
+def grid_pairs_4x4x2():
+    """The 112 overlapping pairs of a 4x4x2 tile grid (BASELINE configs[1]): 64 face neighbours plus the 48
+    xz / yz edge neighbours."""
+    def tid(i, j, k):
+        return (k * 4 + j) * 4 + i
+    pairs = []
+    for k in range(2):
+        for j in range(4):
+            for i in range(4):
+                if i < 3:
+                    pairs.append((tid(i, j, k), tid(i + 1, j, k)))
+                if j < 3:
+                    pairs.append((tid(i, j, k), tid(i, j + 1, k)))
+                if k < 1:
+                    pairs.append((tid(i, j, k), tid(i, j, k + 1)))
+                if i < 3 and k < 1:
+                    pairs.append((tid(i, j, k), tid(i + 1, j, k + 1)))
+                    pairs.append((tid(i + 1, j, k), tid(i, j, k + 1)))
+                if j < 3 and k < 1:
+                    pairs.append((tid(i, j, k), tid(i, j + 1, k + 1)))
+                    pairs.append((tid(i, j + 1, k), tid(i, j, k + 1)))
+    assert len(pairs) == 112
+    return pairs
+
+
+def make_pcm_grid_workload(n=512, device="cuda", seed=43, max_shift=10, n_tiles=32):
+    """End-to-end form of config 2: 32 tiles of n^3 uint16 (a 4x4x2 grid), every tile a crop of ONE field at its
+    own planted offset s_t, so that any pair (a, b) has the true shift s_b - s_a.  Returns (tiles, offsets_xyz)."""
+    rng = np.random.default_rng(seed)
+    offs = rng.integers(-max_shift, max_shift + 1, size=(n_tiles, 3))
+    m = max_shift + 2
+    fld = smooth_field((n + 2 * m,) * 3, 3000, device)
+    tiles = [tile_from_field(fld, (m + int(o[2]), m + int(o[1]), m + int(o[0])), (n, n, n), 200000 + t)
+             for t, o in enumerate(offs)]
+    return tiles, [tuple(int(v) for v in o) for o in offs]
 
 
 def make_fusion_workload(grid=(4, 4, 4), tile=576, stride=491, device="cuda", n_distinct=4, seed=7,

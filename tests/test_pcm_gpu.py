@@ -224,7 +224,7 @@ def test_volumes_batch_crops_on_device(ctx):
     assert got[0] == ctx.pcm_pair(a, b)
     o = po.pcm_shift(a, b)
     assert got[0].found and got[0].shift_int == o.shift_int and abs(got[0].r - o.r) < 1e-9
-    assert got[0].shift_int == (-4, 3, -2)      # planted: B's content sits 4 px further right than the nominal 66
+    assert got[0].shift_int == (4, -3, 2)       # planted: b[p] = a[p + (4, -3, 2)] (true x offset 70 vs nominal 66)
     assert got[1].shift_int == (0, 0, 0) and abs(got[1].r - 1.0) < 1e-12
     assert got[2] == ctx.pcm_pair(b, a)
     ctx.volume_free(hA)
