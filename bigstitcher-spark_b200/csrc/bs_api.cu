@@ -341,7 +341,17 @@ int bs_volume_devptr(bs_ctx* ctx, unsigned long long handle, void** dev) {
     return BS_OK;
 }
 
-int bs_volume_download(bs_ctx* ctx, unsigned long long handle, void* host) {
+int bs_volume_info(bs_ctx* ctx, unsigned long long handle, long long dims[3], int* dtype) {
+    if (!ctx) return BS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->vols.find(handle);
+    if (it == ctx->vols.end()) return bs_set_error(ctx, BS_ERR_ARG, "bs_volume_info: unknown handle %llu", handle);
+    if (dims) for (int d = 0; d < 3; ++d) dims[d] = it->second.dims[d];
+    if (dtype) *dtype = it->second.dtype;
+    return BS_OK;
+}
+
+int bs_volume_download(bs_ctx* ctx, unsigned long long handle, void* host, unsigned long long capacity_bytes) {
     if (!ctx) return BS_ERR_ARG;
     std::lock_guard<std::mutex> lk(ctx->mu);
     auto it = ctx->vols.find(handle);
@@ -349,6 +359,8 @@ int bs_volume_download(bs_ctx* ctx, unsigned long long handle, void* host) {
         return bs_set_error(ctx, BS_ERR_ARG, "bs_volume_download: unknown handle or NULL host");
     bs_volume& v = it->second;
     size_t bytes = (size_t)v.dims[0] * v.dims[1] * v.dims[2] * dtype_size(v.dtype);
+    if (capacity_bytes < bytes)
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_volume_download: buffer of %llu bytes, volume needs %zu", capacity_bytes, bytes);
     BS_CUDA(ctx, cudaSetDevice(ctx->device));
     { int rc = bs_volume_acquire(ctx, v); if (rc) return rc; }
     BS_CUDA(ctx, cudaMemcpyAsync(host, v.dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));

@@ -3,8 +3,8 @@ Appendix B; n5 3.5.0, pom.xml:109-111).
 
 Covers what `stitching` / `affine-fusion` touch: dataset `attributes.json`, block files
 `<dataset>/<gx>/<gy>/<gz>` with the big-endian header (uint16 mode, uint16 ndim, ndim x uint32
-block dims) followed by big-endian x-fastest elements, `raw` and `gzip` compression (zstd, the
-reference's default, is not available in this image: J/CreateFusionContainer.java:71-76), the BDV-N5
+block dims) followed by big-endian x-fastest elements, `raw`, `gzip` and `zstd` compression (zstd, the reference's default J/CreateFusionContainer.java:71-76,
+through the in-repo codec zstd.py), the BDV-N5
 input layout `setup{S}/timepoint{T}/s{L}` and the container root attributes `Bigstitcher-Spark/*`
 (J/CreateFusionContainer.java:302-320,519; read back at J/SparkAffineFusion.java:241-307).
 Host-side plumbing only -- no voxel arithmetic.
@@ -18,6 +18,25 @@ import struct
 import zlib
 
 import numpy as np
+
+from . import zstd as bzstd
+
+BS_KEY = "Bigstitcher-Spark"
+
+
+def bs_attrs(flat: dict) -> dict:
+    """`setAttribute("/", "Bigstitcher-Spark/InputXML", v)` of N5 3.x treats '/' as a JSON path: the attributes
+    are written as ONE nested object {"Bigstitcher-Spark": {"InputXML": v, ...}} (J/CreateFusionContainer.java:302-320)."""
+    return {BS_KEY: dict(flat)}
+
+
+def bs_attr_get(attrs: dict, key, default=None):
+    """Read `Bigstitcher-Spark/<key>`: the nested form the reference writes, or the flat key with a literal slash
+    that round-1 containers of this build used."""
+    nested = attrs.get(BS_KEY)
+    if isinstance(nested, dict) and key in nested:
+        return nested[key]
+    return attrs.get(BS_KEY + "/" + key, default)
 
 _DTYPES = {"uint8": np.uint8, "uint16": np.uint16, "uint32": np.uint32, "int16": np.int16,
            "float32": np.float32, "float64": np.float64}
@@ -58,7 +77,11 @@ class N5Store:
         p = self._attr_path(group)
         os.makedirs(os.path.dirname(p), exist_ok=True)
         cur = self.get_attributes(group)
-        cur.update(attrs)
+        for k, v in attrs.items():
+            if k == BS_KEY and isinstance(v, dict) and isinstance(cur.get(k), dict):
+                cur[k].update(v)
+            else:
+                cur[k] = v
         with open(p, "w") as f:
             json.dump(cur, f)
 
@@ -67,6 +90,8 @@ class N5Store:
         comp = {"type": compression}
         if compression == "gzip":
             comp["level"] = 1  # reference default, J/util/N5Util.java:82-105
+        elif compression == "zstd":
+            comp["level"] = 3  # reference default (J/CreateFusionContainer.java:71-76, J/util/N5Util.java:91-92)
         self.set_attributes(path, {"dimensions": [int(d) for d in dimensions],
                                    "blockSize": [int(b) for b in block_size],
                                    "dataType": _dtype_name(dtype), "compression": comp})
@@ -92,6 +117,8 @@ class N5Store:
         ctype = a["compression"]["type"]
         if ctype == "gzip":
             payload = gzip.compress(payload, compresslevel=a["compression"].get("level", 1))
+        elif ctype == "zstd":
+            payload = bzstd.compress(payload)
         elif ctype != "raw":
             raise NotImplementedError(f"compression {ctype} (not available in this image)")
         p = self._block_path(path, grid_pos)
@@ -115,6 +142,8 @@ class N5Store:
         ctype = a["compression"]["type"]
         if ctype == "gzip":
             payload = zlib.decompress(payload, 16 + zlib.MAX_WBITS)
+        elif ctype == "zstd":
+            payload = bzstd.decompress(payload)
         elif ctype != "raw":
             raise NotImplementedError(f"compression {ctype}")
         dt = np.dtype(_DTYPES[a["dataType"]])
@@ -136,6 +165,34 @@ class N5Store:
                         continue
                     z, y, x = b.shape
                     out[gz * bs[2]:gz * bs[2] + z, gy * bs[1]:gy * bs[1] + y, gx * bs[0]:gx * bs[0] + x] = b
+        return out
+
+    def read_region(self, path, min_xyz, size_xyz):
+        """[z, y, x] array of the interval [min, min + size) -- only the storage blocks it touches are read
+        (missing blocks / parts outside the dataset are zero)."""
+        a = self.dataset_attributes(path)
+        dims, bs = a["dimensions"], a["blockSize"]
+        mn = [int(v) for v in min_xyz]
+        sz = [int(v) for v in size_xyz]
+        out = np.zeros(sz[::-1], dtype=_DTYPES[a["dataType"]])
+        lo = [max(0, mn[d]) for d in range(3)]
+        hi = [min(dims[d], mn[d] + sz[d]) for d in range(3)]     # exclusive
+        if any(hi[d] <= lo[d] for d in range(3)):
+            return out
+        for gz in range(lo[2] // bs[2], -(-hi[2] // bs[2])):
+            for gy in range(lo[1] // bs[1], -(-hi[1] // bs[1])):
+                for gx in range(lo[0] // bs[0], -(-hi[0] // bs[0])):
+                    b = self.read_block(path, (gx, gy, gz))
+                    if b is None:
+                        continue
+                    b0 = (gx * bs[0], gy * bs[1], gz * bs[2])
+                    bz, by, bx = b.shape
+                    s0 = [max(lo[d], b0[d]) for d in range(3)]
+                    s1 = [min(hi[0], b0[0] + bx), min(hi[1], b0[1] + by), min(hi[2], b0[2] + bz)]
+                    if any(s1[d] <= s0[d] for d in range(3)):
+                        continue
+                    out[s0[2] - mn[2]:s1[2] - mn[2], s0[1] - mn[1]:s1[1] - mn[1], s0[0] - mn[0]:s1[0] - mn[0]] = \
+                        b[s0[2] - b0[2]:s1[2] - b0[2], s0[1] - b0[1]:s1[1] - b0[1], s0[0] - b0[0]:s1[0] - b0[0]]
         return out
 
     def save_block(self, path, volume: np.ndarray, grid_offset):
@@ -202,34 +259,37 @@ def create_fusion_container(root, input_xml, bb_min, bb_max, block_size=(128, 12
                                "relativeDownsampling": [int(v) for v in rel], "absoluteDownsampling": list(absd),
                                "dataType": dtype})
             mr.append(levels)
-    attrs = {"Bigstitcher-Spark/FusionFormat": "N5", "Bigstitcher-Spark/InputXML": input_xml,
-             "Bigstitcher-Spark/NumTimepoints": num_timepoints, "Bigstitcher-Spark/NumChannels": num_channels,
-             "Bigstitcher-Spark/Boundingbox_min": [int(v) for v in bb_min],
-             "Bigstitcher-Spark/Boundingbox_max": [int(v) for v in bb_max],
-             "Bigstitcher-Spark/PreserveAnisotropy": anisotropy_factor is not None,
-             "Bigstitcher-Spark/DataType": dtype.upper(), "Bigstitcher-Spark/BlockSize": list(block_size),
-             "Bigstitcher-Spark/MultiResolutionInfos": mr}
+    flat = {"FusionFormat": "N5", "InputXML": input_xml, "NumTimepoints": num_timepoints, "NumChannels": num_channels,
+            "Boundingbox_min": [int(v) for v in bb_min], "Boundingbox_max": [int(v) for v in bb_max],
+            "PreserveAnisotropy": anisotropy_factor is not None,
+            "DataType": dtype.lower(),      # N5's DataType adapter (de)serialises lowercase names
+            "BlockSize": list(block_size), "MultiResolutionInfos": mr}
     if anisotropy_factor is not None:
-        attrs["Bigstitcher-Spark/AnisotropyFactor"] = float(anisotropy_factor)
+        flat["AnisotropyFactor"] = float(anisotropy_factor)
     if dtype != "float32":
-        attrs["Bigstitcher-Spark/MinIntensity"] = float(min_intensity)
-        attrs["Bigstitcher-Spark/MaxIntensity"] = float(max_intensity)
+        flat["MinIntensity"] = float(min_intensity)
+        flat["MaxIntensity"] = float(max_intensity)
+    attrs = bs_attrs(flat)
     store.set_attributes("", attrs)
     return store
+
+
+def parse_fusion_metadata(a: dict):
+    """Bigstitcher-Spark/* -> the dict `affine-fusion` works with (J/SparkAffineFusion.java:241-307)."""
+    g = lambda k, d=None: bs_attr_get(a, k, d)  # noqa: E731
+    if g("FusionFormat") is None:
+        raise KeyError("not a BigStitcher-Spark fusion container (no Bigstitcher-Spark/FusionFormat)")
+    return {
+        "format": g("FusionFormat"), "input_xml": g("InputXML"), "num_timepoints": g("NumTimepoints", 1),
+        "num_channels": g("NumChannels", 1), "bb_min": g("Boundingbox_min"), "bb_max": g("Boundingbox_max"),
+        "preserve_anisotropy": g("PreserveAnisotropy", False), "anisotropy_factor": g("AnisotropyFactor", float("nan")),
+        "dtype": str(g("DataType", "float32")).lower(), "block_size": g("BlockSize"),
+        "min_intensity": g("MinIntensity", 0.0), "max_intensity": g("MaxIntensity", 65535.0),
+        "mr_infos": g("MultiResolutionInfos"),
+    }
 
 
 def read_fusion_container(root):
     """The metadata `affine-fusion` needs (J/SparkAffineFusion.java:241-307)."""
     store = N5Store(root)
-    a = store.get_attributes("")
-    g = lambda k, d=None: a.get("Bigstitcher-Spark/" + k, d)  # noqa: E731
-    if g("FusionFormat") is None:
-        raise KeyError("not a BigStitcher-Spark fusion container (no Bigstitcher-Spark/FusionFormat)")
-    return store, {
-        "format": g("FusionFormat"), "input_xml": g("InputXML"), "num_timepoints": g("NumTimepoints", 1),
-        "num_channels": g("NumChannels", 1), "bb_min": g("Boundingbox_min"), "bb_max": g("Boundingbox_max"),
-        "preserve_anisotropy": g("PreserveAnisotropy", False), "anisotropy_factor": g("AnisotropyFactor", float("nan")),
-        "dtype": g("DataType", "FLOAT32").lower(), "block_size": g("BlockSize"),
-        "min_intensity": g("MinIntensity", 0.0), "max_intensity": g("MaxIntensity", 65535.0),
-        "mr_infos": g("MultiResolutionInfos"),
-    }
+    return store, parse_fusion_metadata(store.get_attributes(""))

@@ -86,7 +86,7 @@ SYMBOLS = [
     "bs_profile_enable", "bs_profile_reset", "bs_profile_get", "bs_host_alloc", "bs_host_free",
     "bs_pcm_default_params", "bs_pcm_pair", "bs_pcm_batch", "bs_pcm_volumes_batch", "bs_good_fft_size", "bs_pcm_debug_pcm",
     "bs_fuse_default_params", "bs_volume_upload", "bs_volume_upload_async", "bs_volume_wrap", "bs_volume_free",
-    "bs_content_weights", "bs_volume_download", "bs_volume_devptr", "bs_downsample", "bs_fuse_block", "bs_fuse_blocks",
+    "bs_content_weights", "bs_volume_info", "bs_volume_download", "bs_volume_devptr", "bs_downsample", "bs_fuse_block", "bs_fuse_blocks",
     "bs_fuse_block_to_volume", "bs_fuse_accumulate", "bs_fuse_finish",
 ]
 
@@ -131,7 +131,8 @@ def load_library():
     lib.bs_volume_wrap.argtypes = [vp, vp, P(ll), ip, P(ull)]
     lib.bs_volume_free.argtypes = [vp, ull]
     lib.bs_content_weights.argtypes = [vp, ull, dbl, dbl, P(ull)]
-    lib.bs_volume_download.argtypes = [vp, ull, vp]
+    lib.bs_volume_info.argtypes = [vp, ull, P(ll), P(ip)]
+    lib.bs_volume_download.argtypes = [vp, ull, vp, ull]
     lib.bs_volume_devptr.argtypes = [vp, ull, P(vp)]
     lib.bs_downsample.argtypes = [vp, ull, P(ip), P(ull)]
     lib.bs_fuse_block.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), vp, ip]
@@ -351,9 +352,22 @@ class Context:
         self._check(self.lib.bs_content_weights(self.h, handle, float(sigma1), float(sigma2), C.byref(h)))
         return h.value
 
-    def volume_download(self, handle: int, dims_xyz, dtype=np.float32) -> np.ndarray:
-        out = np.empty(tuple(dims_xyz)[::-1], dtype=dtype)
-        self._check(self.lib.bs_volume_download(self.h, handle, out.ctypes.data))
+    def volume_info(self, handle: int):
+        """(dims_xyz, numpy dtype) of a resident volume."""
+        dims = (C.c_longlong * 3)()
+        dt = C.c_int()
+        self._check(self.lib.bs_volume_info(self.h, handle, dims, C.byref(dt)))
+        return tuple(int(v) for v in dims), _BS2NP[dt.value]
+
+    def volume_download(self, handle: int, dims_xyz=None, dtype=None) -> np.ndarray:
+        """Shape and dtype come from the handle; ``dims_xyz`` / ``dtype`` are only checked when given."""
+        dims, dt = self.volume_info(handle)
+        if dims_xyz is not None and tuple(int(v) for v in dims_xyz) != dims:
+            raise ValueError(f"volume {handle} has dims {dims}, caller expected {tuple(dims_xyz)}")
+        if dtype is not None and np.dtype(dtype) != dt:
+            raise ValueError(f"volume {handle} has dtype {dt}, caller expected {np.dtype(dtype)}")
+        out = np.empty(dims[::-1], dtype=dt)
+        self._check(self.lib.bs_volume_download(self.h, handle, out.ctypes.data, out.nbytes))
         return out
 
     @staticmethod

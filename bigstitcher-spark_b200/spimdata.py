@@ -98,6 +98,16 @@ class SpimData2:
     def view_ids(self):
         return sorted(self.registrations)
 
+    def channels_ordered(self):
+        """sd.getAllChannelsOrdered(): the distinct channel ids in ascending order (J/SparkAffineFusion.java:420-421)."""
+        return sorted({s.attributes.get("channel", 0) for s in self.setups.values()})
+
+    def views_of(self, channel_index: int, timepoint_index: int):
+        """The views `affine-fusion` fuses into the (channel, timepoint) volume (J/SparkAffineFusion.java:425-440)."""
+        ch = self.channels_ordered()[channel_index]
+        tp = self.timepoints[timepoint_index]
+        return [v for v in self.view_ids() if v[0] == tp and self.setups[v[1]].attributes.get("channel", 0) == ch]
+
     # ------------------------------------------------------------------ pair construction (row a1)
     def stitching_pairs(self):
         """All tile pairs per (timepoint, angle, channel, illumination) whose transformed bounding
@@ -127,6 +137,37 @@ class SpimData2:
                     pairs.append((a, b))
         return pairs
 
+    def stitching_groups(self):
+        """SpimDataFilteringAndGrouping with the reference's defaults (J/SparkPairwiseStitching.java:141-162): views are
+        GROUPED over {channel, illumination}, COMPARED across tiles, per (timepoint, angle).  Returns the overlapping
+        pairs of groups: [(groupA, groupB)], a group = ascending list of ViewIds of one tile; non-overlapping
+        comparisons are dropped (TransformationTools.filterNonOverlappingPairs, :165)."""
+        groups = {}
+        for (tp, s) in self.view_ids():
+            a = self.setups[s].attributes
+            groups.setdefault((tp, a.get("angle", 0), a.get("tile", s)), []).append((tp, s))
+        keys = sorted(groups)
+        boxes = {}
+        for k in keys:
+            lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+            for (tp, s) in groups[k]:
+                M = self.model(tp, s)
+                dx, dy, dz = self.setups[s].size
+                c = np.array([[x, y, z] for x in (0, dx - 1) for y in (0, dy - 1) for z in (0, dz - 1)], dtype=np.float64)
+                w = c @ M[:, :3].T + M[:, 3]
+                lo, hi = np.minimum(lo, w.min(axis=0)), np.maximum(hi, w.max(axis=0))
+            boxes[k] = (lo, hi)
+        pairs = []
+        for i, ka in enumerate(keys):
+            for kb in keys[i + 1:]:
+                if ka[:2] != kb[:2]:
+                    continue
+                lo = np.maximum(boxes[ka][0], boxes[kb][0])
+                hi = np.minimum(boxes[ka][1], boxes[kb][1])
+                if np.all(hi >= lo):
+                    pairs.append((sorted(groups[ka]), sorted(groups[kb])))
+        return pairs
+
     # ------------------------------------------------------------------ stitching results (rows a6, f-2)
     @staticmethod
     def transform_hash(reg_a, reg_b) -> float:
@@ -140,14 +181,39 @@ class SpimData2:
                 h += float(np.sum(m * (np.arange(12).reshape(3, 4) + 1 + 13 * i)))
         return h
 
+    @staticmethod
+    def _group_of(pr, side):
+        """ViewIds of one side of a <PairwiseResult>: upstream writes comma-separated lists for grouped views."""
+        tps = [int(v) for v in pr.get("tp_" + side).split(",")]
+        sts = [int(v) for v in pr.get("view_setup_" + side).split(",")]
+        if len(tps) == 1 and len(sts) > 1:
+            tps = tps * len(sts)
+        return tuple(sorted(zip(tps, sts)))
+
+    @staticmethod
+    def _as_group(g):
+        return tuple(sorted(g)) if isinstance(g[0], (tuple, list)) else (tuple(g),)
+
+    def remove_stitching_results(self, pairs):
+        """Drop stored results a->b and b->a for every COMPARED pair, including those that found no shift
+        (J/SparkPairwiseStitching.java:323-325)."""
+        sr = self.root.find("StitchingResults")
+        if sr is None:
+            return
+        keys = {frozenset((self._as_group(a), self._as_group(b))) for a, b in pairs}
+        for pr in list(sr.findall("PairwiseResult")):
+            if frozenset((self._group_of(pr, "a"), self._group_of(pr, "b"))) in keys:
+                sr.remove(pr)
+
     def stitching_results(self):
         out = []
         sr = self.root.find("StitchingResults")
         if sr is None:
             return out
         for pr in sr.findall("PairwiseResult"):
-            a = (int(pr.get("tp_a")), int(pr.get("view_setup_a")))
-            b = (int(pr.get("tp_b")), int(pr.get("view_setup_b")))
+            ga, gb = self._group_of(pr, "a"), self._group_of(pr, "b")
+            a = ga[0] if len(ga) == 1 else ga
+            b = gb[0] if len(gb) == 1 else gb
             shift = np.array([float(v) for v in pr.findtext("shift").split()]).reshape(3, 4)
             bb = [float(v) for v in (pr.findtext("overlap_boundingbox") or "").split()]
             out.append(dict(pair=(a, b), shift=shift, r=float(pr.findtext("correlation")),
@@ -162,13 +228,11 @@ class SpimData2:
         if sr is None:
             sr = ET.SubElement(self.root, "StitchingResults")
         for res in results:
-            (tpa, sa), (tpb, sb) = res["pair"]
-            for pr in list(sr.findall("PairwiseResult")):
-                ka = (int(pr.get("tp_a")), int(pr.get("view_setup_a")))
-                kb = (int(pr.get("tp_b")), int(pr.get("view_setup_b")))
-                if {ka, kb} == {(tpa, sa), (tpb, sb)}:
-                    sr.remove(pr)
-            pr = ET.SubElement(sr, "PairwiseResult", view_setup_a=str(sa), view_setup_b=str(sb), tp_a=str(tpa), tp_b=str(tpb))
+            ga, gb = self._as_group(res["pair"][0]), self._as_group(res["pair"][1])
+            self.remove_stitching_results([(ga, gb)])
+            pr = ET.SubElement(sr, "PairwiseResult",
+                               view_setup_a=",".join(str(v[1]) for v in ga), view_setup_b=",".join(str(v[1]) for v in gb),
+                               tp_a=",".join(str(v[0]) for v in ga), tp_b=",".join(str(v[0]) for v in gb))
             sh = ET.SubElement(pr, "shift", type="affine")
             sh.text = _fmt(np.asarray(res["shift"]).ravel())
             ET.SubElement(pr, "correlation").text = repr(float(res["r"]))

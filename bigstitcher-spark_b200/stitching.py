@@ -247,16 +247,132 @@ def filter_results(results, min_r=0.3, max_r=1.0, max_shift_xyz=None, max_shift_
     return kept
 
 
-def stitch_pairs(pairs, tiles, models, params=None, downsample_factors=(1, 1, 1), ctx: Context | None = None):
-    """The collapsed RDD (J/SparkPairwiseStitching.java:192-312): a plain host work queue over
-    tile pairs.  ``pairs``: [(idA, idB)], ``tiles``: id -> [z,y,x] array, ``models``: id -> 3x4."""
+def aggregate_views(images: dict, attributes: dict, channel_combine="AVERAGE", illum_combine="PICK_BRIGHTEST"):
+    """GroupedViewAggregator with the reference's two actions in its order (J/SparkPairwiseStitching.java:204-208):
+    first the illuminations of every channel are combined (default PICK_BRIGHTEST), then the channels (default
+    AVERAGE).  images: ViewId -> [z,y,x] array of one group; attributes: ViewId -> {"channel": c, "illumination": i}."""
+    by_channel = {}
+    for vid in sorted(images):
+        by_channel.setdefault(attributes.get(vid, {}).get("channel", 0), []).append(images[vid])
+    per_channel = [aggregate_group(by_channel[c], illum_combine) for c in sorted(by_channel)]
+    return aggregate_group(per_channel, channel_combine)
+
+
+def _is_group(x):
+    return isinstance(x, (list, tuple)) and len(x) > 0 and isinstance(x[0], (list, tuple))
+
+
+def stitch_pairs(pairs, tiles, models, params=None, downsample_factors=(1, 1, 1), ctx: Context | None = None,
+                 attributes: dict | None = None, channel_combine="AVERAGE", illum_combine="PICK_BRIGHTEST",
+                 max_resident_bytes=64 << 30):
+    """The collapsed RDD (J/SparkPairwiseStitching.java:192-312): a host work queue over pairs of view GROUPS.
+    ``pairs``: [(A, B)] where A / B is a ViewId or a list of ViewIds (one tile's channels / illuminations);
+    ``tiles``: ViewId -> [z,y,x] array; ``models``: ViewId -> 3x4; ``attributes``: ViewId -> channel / illumination.
+
+    Every group is aggregated + downsampled ONCE, uploaded ONCE (async, from pinned memory when available) and
+    stays resident while its pairs run; the overlap crops are cut on the device (bs_pcm_volumes_batch).  Pairs whose
+    non-translation parts differ go through the virtual-fusion branch one by one."""
     params = params or PairwiseStitchingParameters()
-    out = []
-    for (ia, ib) in pairs:
-        r = compute_stitching(tiles[ia], tiles[ib], models[ia], models[ib], params, downsample_factors, ctx)
-        if r is None:
-            out.append(None)
+    attributes = attributes or {}
+    ds = np.asarray(downsample_factors, dtype=np.float64)
+    groups = [(tuple(a) if _is_group(a) else (tuple(a),), tuple(b) if _is_group(b) else (tuple(b),)) for a, b in pairs]
+
+    def first(g):
+        return g[0]
+
+    def pair_id(g):
+        return g[0] if len(g) == 1 else g
+
+    cache = {}
+
+    def group_image(g):
+        if g not in cache:
+            img = tiles[g[0]] if len(g) == 1 else aggregate_views({v: tiles[v] for v in g}, attributes, channel_combine, illum_combine)
+            cache[g] = downsample_avg(img, downsample_factors) if isinstance(img, np.ndarray) else img
+        return cache[g]
+
+    out = [None] * len(groups)
+    fast = []      # (index, gA, gB, interval1, interval2, size, sub1, sub2)
+    for i, (ga, gb) in enumerate(groups):
+        ma = np.asarray(models[first(ga)], dtype=np.float64).reshape(3, 4)
+        mb = np.asarray(models[first(gb)], dtype=np.float64).reshape(3, 4)
+        if not non_translations_equal(ma, mb):
+            r = compute_stitching_non_equal_transformations(group_image(ga) if len(ga) > 1 else tiles[ga[0]],
+                                                            group_image(gb) if len(gb) > 1 else tiles[gb[0]],
+                                                            ma, mb, params, downsample_factors, ctx)
+            if r is not None:
+                (tr, cc), (bmin, bmax) = r
+                out[i] = PairwiseStitchingResult((pair_id(ga), pair_id(gb)), tr, cc, bmin, bmax, shift_px=tuple(tr[:, 3]))
             continue
-        (tr, cc), (bmin, bmax) = r
-        out.append(PairwiseStitchingResult((ia, ib), tr, cc, bmin, bmax, shift_px=tuple(tr[:, 3])))
+        dims_a = tuple(tiles[first(ga)].shape)[::-1]
+        dims_b = tuple(tiles[first(gb)].shape)[::-1]
+        la, ha = _world_box(ma, dims_a)
+        lb, hb = _world_box(mb, dims_b)
+        ov = _overlap(la, ha, lb, hb)
+        if ov is None:
+            continue
+        lin_inv = np.linalg.inv(ma[:, :3])
+        t1 = (lin_inv @ ma[:, 3]) / ds
+        t2 = (lin_inv @ mb[:, 3]) / ds
+        da = tuple(int(dims_a[d] // int(ds[d])) for d in range(3))
+        db = tuple(int(dims_b[d] // int(ds[d])) for d in range(3))
+        ro = local_raster_overlaps(da, db, t1, t2)
+        if ro is None:
+            continue
+        fast.append((i, ga, gb, ro, ov, mb))
+
+    # resident-tile batches: greedily fill the device budget, upload, correlate, free
+    p = ctx.pcm_params(params.peaks_to_check, params.do_subpixel, params.min_overlap, params.extension) if fast else None
+    pos = 0
+    while pos < len(fast):
+        need, nbytes, end = {}, 0, pos
+        while end < len(fast):
+            extra = [g for g in (fast[end][1], fast[end][2]) if g not in need]
+            add = sum(group_image(g).nbytes for g in set(extra))
+            if need and nbytes + add > max_resident_bytes:
+                break
+            for g in extra:
+                need[g] = True
+            nbytes += add
+            end += 1
+        handles = {}
+        try:
+            for g in need:
+                img = np.ascontiguousarray(group_image(g))
+                cache[g] = img
+                handles[g] = ctx.volume_upload(img)
+            by_dtype = {}
+            for item in fast[pos:end]:
+                by_dtype.setdefault((group_image(item[1]).dtype, group_image(item[2]).dtype), []).append(item)
+            for (dta, dtb), items in by_dtype.items():
+                if dta != dtb:   # one side averaged (float32), the other a single uint16 view: host crops
+                    for (i, ga, gb, ro, ov, mb) in items:
+                        a1, a2, size, sub1, sub2 = ro
+                        A, B = group_image(ga), group_image(gb)
+                        c1 = np.ascontiguousarray(A[a1[2]:a1[2] + size[2], a1[1]:a1[1] + size[1], a1[0]:a1[0] + size[0]], dtype=np.float32)
+                        c2 = np.ascontiguousarray(B[a2[2]:a2[2] + size[2], a2[1]:a2[1] + size[1], a2[0]:a2[0] + size[0]], dtype=np.float32)
+                        res = [ctx.pcm_pair(c1, c2, p)]
+                        _finish_fast(out, [(i, ga, gb, ro, ov, mb)], res, params, ds, pair_id)
+                    continue
+                jobs = [(handles[ga], handles[gb], tuple(int(v) for v in ro[0]), tuple(int(v) for v in ro[1]),
+                         tuple(int(v) for v in ro[2])) for (_, ga, gb, ro, _, _) in items]
+                _finish_fast(out, items, ctx.pcm_volumes_batch(jobs, p), params, ds, pair_id)
+        finally:
+            for h in handles.values():
+                ctx.volume_free(h)
+        pos = end
     return out
+
+
+def _finish_fast(out, items, results, params, ds, pair_id):
+    for (i, ga, gb, ro, ov, mb), res in zip(items, results):
+        if not res.found or math.isinf(res.r):
+            continue
+        s = np.asarray(res.shift_sub if params.do_subpixel else res.shift_int, dtype=np.float64)
+        shift = s - (np.asarray(ro[4]) - np.asarray(ro[3]))     # int / real coordinate difference of the raster crops
+        T = np.eye(4)
+        T[:3, 3] = shift * ds
+        Mb = np.vstack([mb, [0, 0, 0, 1]])
+        R = (Mb @ T @ np.linalg.inv(Mb))[:3, :].copy()
+        out[i] = PairwiseStitchingResult((pair_id(ga), pair_id(gb)), R, float(res.r), tuple(ov[0]), tuple(ov[1]),
+                                         shift_px=tuple(R[:, 3]))

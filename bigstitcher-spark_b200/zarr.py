@@ -3,8 +3,8 @@ container (J/CreateFusionContainer.java:67-69,331-389): one 5-D array per resolu
 axis order x,y,z,c,t == Zarr array order t,c,z,y,x, chunks {1,1,bz,by,bx}, levels named "0","1",...
 (:346), `multiscales` v0.4 metadata (:374-388), grid offsets {gx,gy,gz,c,t} at write time
 (J/SparkAffineFusion.java:630-643).  Little-endian C-order chunks, always full chunk shape (edge
-chunks padded with fill_value 0), dimension_separator "/"; compressor null (raw) or gzip -- zstd,
-the reference default, is not available in this image.  Host-side plumbing only.
+chunks padded with fill_value 0), dimension_separator "/"; compressor null (raw), gzip or zstd (the reference default,
+through zstd.py).  Host-side plumbing only.
 """
 from __future__ import annotations
 
@@ -13,6 +13,9 @@ import json
 import os
 
 import numpy as np
+
+from . import zstd as bzstd
+from .n5 import bs_attrs, parse_fusion_metadata, BS_KEY
 
 _ZDT = {"uint8": "|u1", "uint16": "<u2", "float32": "<f4"}
 _NPDT = {"|u1": np.uint8, "<u2": np.uint16, "<f4": np.float32}
@@ -45,13 +48,18 @@ class ZarrStore:
 
     def set_attributes(self, group, attrs: dict):
         cur = self.get_attributes(group)
-        cur.update(attrs)
+        for k, v in attrs.items():
+            if k == BS_KEY and isinstance(v, dict) and isinstance(cur.get(k), dict):
+                cur[k].update(v)
+            else:
+                cur[k] = v
         self._write_json(group, ".zattrs", cur)
 
     def create_array(self, path, shape_tczyx, chunks_tczyx, dtype: str, compression="raw"):
-        comp = None if compression == "raw" else {"id": "gzip", "level": 1}
-        if compression not in ("raw", "gzip"):
+        if compression not in ("raw", "gzip", "zstd"):
             raise NotImplementedError(f"compression {compression} (not available in this image)")
+        # numcodecs ids; zstd level 3 = the reference default (J/util/N5Util.java:91-92)
+        comp = {"raw": None, "gzip": {"id": "gzip", "level": 1}, "zstd": {"id": "zstd", "level": 3}}[compression]
         self._write_json(path, ".zarray", {"zarr_format": 2, "shape": [int(v) for v in shape_tczyx],
                                            "chunks": [int(v) for v in chunks_tczyx], "dtype": _ZDT[dtype],
                                            "compressor": comp, "fill_value": 0, "order": "C", "filters": None,
@@ -76,7 +84,10 @@ class ZarrStore:
         full[:z, :y, :x] = block_zyx
         payload = full.astype(dt.newbyteorder("<"), copy=False).tobytes()
         if m["compressor"] is not None:
-            payload = gzip.compress(payload, compresslevel=m["compressor"].get("level", 1))
+            if m["compressor"]["id"] == "zstd":
+                payload = bzstd.compress(payload, m["compressor"].get("level", 3))
+            else:
+                payload = gzip.compress(payload, compresslevel=m["compressor"].get("level", 1))
         p = self._chunk_path(path, idx_tczyx)
         os.makedirs(os.path.dirname(p), exist_ok=True)
         with open(p, "wb") as f:
@@ -92,7 +103,7 @@ class ZarrStore:
         with open(p, "rb") as f:
             payload = f.read()
         if m["compressor"] is not None:
-            payload = gzip.decompress(payload)
+            payload = bzstd.decompress(payload) if m["compressor"]["id"] == "zstd" else gzip.decompress(payload)
         return np.frombuffer(payload, dtype=dt.newbyteorder("<")).astype(dt).reshape(cz, cy, cx)
 
     def save_block(self, path, volume_zyx: np.ndarray, grid_offset_xyzct):
@@ -113,6 +124,29 @@ class ZarrStore:
                     blk = blk[:sz - iz * cz, :sy - iy * cy, :sx - ix * cx]
                     self.write_chunk(path, (t, c, iz, iy, ix), blk)
 
+    def read_region(self, path, min_xyz, size_xyz, c=0, t=0):
+        """[z, y, x] array of the interval [min, min + size) of channel c / timepoint t (zero outside the array)."""
+        m = self.array_meta(path)
+        sz, sy, sx = m["shape"][2:]
+        cz, cy, cx = m["chunks"][2:]
+        mn = [int(v) for v in min_xyz]
+        n = [int(v) for v in size_xyz]
+        out = np.zeros(n[::-1], dtype=_NPDT[m["dtype"]])
+        lo = [max(0, mn[d]) for d in range(3)]
+        hi = [min((sx, sy, sz)[d], mn[d] + n[d]) for d in range(3)]
+        if any(hi[d] <= lo[d] for d in range(3)):
+            return out
+        for iz in range(lo[2] // cz, -(-hi[2] // cz)):
+            for iy in range(lo[1] // cy, -(-hi[1] // cy)):
+                for ix in range(lo[0] // cx, -(-hi[0] // cx)):
+                    ch = self.read_chunk(path, (t, c, iz, iy, ix))
+                    b0 = (ix * cx, iy * cy, iz * cz)
+                    s0 = [max(lo[d], b0[d]) for d in range(3)]
+                    s1 = [min(hi[0], b0[0] + cx), min(hi[1], b0[1] + cy), min(hi[2], b0[2] + cz)]
+                    out[s0[2] - mn[2]:s1[2] - mn[2], s0[1] - mn[1]:s1[1] - mn[1], s0[0] - mn[0]:s1[0] - mn[0]] = \
+                        ch[s0[2] - b0[2]:s1[2] - b0[2], s0[1] - b0[1]:s1[1] - b0[1], s0[0] - b0[0]:s1[0] - b0[0]]
+        return out
+
     def read_volume(self, path, c=0, t=0):
         m = self.array_meta(path)
         sz, sy, sx = m["shape"][2:]
@@ -127,54 +161,63 @@ class ZarrStore:
         return out
 
 
+def mipmap_transform_default(abs_ds):
+    """MipmapTransforms.getMipmapTransformDefault: scale f per axis and a half-pixel shift (f - 1) / 2
+    (example at J/SparkInterestPointDetection.java:1073-1080)."""
+    f = [float(v) for v in abs_ds]
+    return [[f[0], 0, 0, (f[0] - 1) / 2], [0, f[1], 0, (f[1] - 1) / 2], [0, 0, f[2], (f[2] - 1) / 2]]
+
+
 def create_fusion_container_zarr(root, input_xml, bb_min, bb_max, block_size=(128, 128, 128), dtype="float32",
                                  min_intensity=None, max_intensity=None, num_timepoints=1, num_channels=1,
-                                 anisotropy_factor=None, compression="raw", voxel_size=(1.0, 1.0, 1.0)):
-    """`create-fusion-container -s ZARR` (J/CreateFusionContainer.java:331-389): 5-D array "0" with the
-    `multiscales` attribute and the `Bigstitcher-Spark/*` root attributes."""
+                                 anisotropy_factor=None, compression="raw", voxel_size=(1.0, 1.0, 1.0),
+                                 downsamplings=()):
+    """`create-fusion-container -s ZARR` (J/CreateFusionContainer.java:331-389): one 5-D array per resolution level
+    ("0", "1", ...: levelToName :346), the OME-NGFF v0.4 `multiscales` attribute with one scale + translation per
+    level (:374-388) and the `Bigstitcher-Spark/*` root attributes.  ``downsamplings``: RELATIVE steps after s0
+    (e.g. [(2,2,1), (2,2,2)]); the 5-D pyramid of N5ApiTools.setupMultiResolutionPyramid never downsamples c / t."""
     st = ZarrStore(root, create=True)
     dims = [int(bb_max[d] - bb_min[d] + 1) for d in range(3)]
-    st.create_array("0", (num_timepoints, num_channels, dims[2], dims[1], dims[0]),
-                    (1, 1, block_size[2], block_size[1], block_size[0]), dtype, compression)
+    levels, datasets = [], []
+    cur, absd = list(dims), [1, 1, 1]
+    for lvl, rel in enumerate([(1, 1, 1)] + [tuple(int(v) for v in r) for r in downsamplings]):
+        if lvl > 0:
+            cur = [cur[d] // rel[d] for d in range(3)]
+            absd = [absd[d] * rel[d] for d in range(3)]
+        st.create_array(str(lvl), (num_timepoints, num_channels, cur[2], cur[1], cur[0]),
+                        (1, 1, block_size[2], block_size[1], block_size[0]), dtype, compression)
+        levels.append({"dataset": str(lvl), "dimensions": list(cur) + [num_channels, num_timepoints],
+                       "blockSize": list(block_size) + [1, 1], "relativeDownsampling": list(rel) + [1, 1],
+                       "absoluteDownsampling": list(absd) + [1, 1], "dataType": dtype})
+        mt = mipmap_transform_default(absd)
+        datasets.append({"path": str(lvl), "coordinateTransformations": [
+            {"type": "scale", "scale": [1.0, 1.0, voxel_size[2] * absd[2], voxel_size[1] * absd[1], voxel_size[0] * absd[0]]},
+            {"type": "translation", "translation": [0.0, 0.0, voxel_size[2] * mt[2][3], voxel_size[1] * mt[1][3],
+                                                    voxel_size[0] * mt[0][3]]}]})
     multiscales = [{"version": "0.4", "name": "/",
                     "axes": [{"name": "t", "type": "time", "unit": "second"}, {"name": "c", "type": "channel"},
                              {"name": "z", "type": "space", "unit": "micrometer"},
                              {"name": "y", "type": "space", "unit": "micrometer"},
                              {"name": "x", "type": "space", "unit": "micrometer"}],
-                    "datasets": [{"path": "0", "coordinateTransformations": [
-                        {"type": "scale", "scale": [1.0, 1.0, voxel_size[2], voxel_size[1], voxel_size[0]]},
-                        {"type": "translation", "translation": [0.0, 0.0, 0.0, 0.0, 0.0]}]}]}]
-    mr = [[{"dataset": "0", "dimensions": dims + [num_channels, num_timepoints],
-            "blockSize": list(block_size) + [1, 1], "relativeDownsampling": [1, 1, 1],
-            "absoluteDownsampling": [1, 1, 1], "dataType": dtype}]]
-    attrs = {"multiscales": multiscales, "Bigstitcher-Spark/FusionFormat": "OME-ZARR",
-             "Bigstitcher-Spark/InputXML": input_xml, "Bigstitcher-Spark/NumTimepoints": num_timepoints,
-             "Bigstitcher-Spark/NumChannels": num_channels,
-             "Bigstitcher-Spark/Boundingbox_min": [int(v) for v in bb_min],
-             "Bigstitcher-Spark/Boundingbox_max": [int(v) for v in bb_max],
-             "Bigstitcher-Spark/PreserveAnisotropy": anisotropy_factor is not None,
-             "Bigstitcher-Spark/DataType": dtype.upper(), "Bigstitcher-Spark/BlockSize": list(block_size),
-             "Bigstitcher-Spark/MultiResolutionInfos": mr}
+                    "datasets": datasets}]
+    flat = {"FusionFormat": "OME-ZARR", "InputXML": input_xml, "NumTimepoints": num_timepoints, "NumChannels": num_channels,
+            "Boundingbox_min": [int(v) for v in bb_min], "Boundingbox_max": [int(v) for v in bb_max],
+            "PreserveAnisotropy": anisotropy_factor is not None, "DataType": dtype.lower(),
+            "BlockSize": list(block_size), "MultiResolutionInfos": [levels]}
     if anisotropy_factor is not None:
-        attrs["Bigstitcher-Spark/AnisotropyFactor"] = float(anisotropy_factor)
+        flat["AnisotropyFactor"] = float(anisotropy_factor)
     if dtype != "float32":
-        attrs["Bigstitcher-Spark/MinIntensity"] = float(min_intensity)
-        attrs["Bigstitcher-Spark/MaxIntensity"] = float(max_intensity)
+        flat["MinIntensity"] = float(min_intensity)
+        flat["MaxIntensity"] = float(max_intensity)
+    attrs = {"multiscales": multiscales}
+    attrs.update(bs_attrs(flat))
     st.set_attributes("", attrs)
     return st
 
 
 def read_fusion_container_zarr(root):
     st = ZarrStore(root)
-    a = st.get_attributes("")
-    g = lambda k, d=None: a.get("Bigstitcher-Spark/" + k, d)  # noqa: E731
-    if g("FusionFormat") != "OME-ZARR":
+    meta = parse_fusion_metadata(st.get_attributes(""))
+    if meta["format"] != "OME-ZARR":
         raise KeyError("not a BigStitcher-Spark OME-ZARR fusion container")
-    return st, {
-        "format": "OME-ZARR", "input_xml": g("InputXML"), "num_timepoints": g("NumTimepoints", 1),
-        "num_channels": g("NumChannels", 1), "bb_min": g("Boundingbox_min"), "bb_max": g("Boundingbox_max"),
-        "preserve_anisotropy": g("PreserveAnisotropy", False), "anisotropy_factor": g("AnisotropyFactor", float("nan")),
-        "dtype": g("DataType", "FLOAT32").lower(), "block_size": g("BlockSize"),
-        "min_intensity": g("MinIntensity", 0.0), "max_intensity": g("MaxIntensity", 65535.0),
-        "mr_infos": g("MultiResolutionInfos"),
-    }
+    return st, meta

@@ -177,7 +177,11 @@ int bs_volume_free(bs_ctx* ctx, unsigned long long handle);
 /* c = G_sigma2 * (I - G_sigma1 * I)^2 on the source volume -> new float32 volume handle */
 int bs_content_weights(bs_ctx* ctx, unsigned long long vol_handle, double sigma1, double sigma2,
                        unsigned long long* content_handle);
-int bs_volume_download(bs_ctx* ctx, unsigned long long handle, void* host);
+/* dims {x,y,z} and dtype of a resident volume (either may be NULL) */
+int bs_volume_info(bs_ctx* ctx, unsigned long long handle, long long dims[3], int* dtype);
+/* copies the whole volume to `host`; capacity_bytes is the size of the caller's buffer and must be at least the
+ * volume's byte size (no silent overflow) */
+int bs_volume_download(bs_ctx* ctx, unsigned long long handle, void* host, unsigned long long capacity_bytes);
 /* next row 8f-3: one 2x half-pixel averaging pyramid step on a resident volume (factors 1 or 2 per
  * axis, output dims = floor(dims / factors), same dtype) -> new handle.  Replaces re-reading level
  * l-1 from the container for every pyramid level (J/SparkAffineFusion.java:703-782). */

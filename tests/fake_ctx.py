@@ -36,6 +36,14 @@ class FakeContext:
         self.calls["pcm"] += 1
         return po.pcm_shift(np.asarray(a), np.asarray(b), **(p or self.pcm_params()))
 
+    def pcm_volumes_batch(self, jobs, p=None):
+        out = []
+        for (v1, v2, m1, m2, d) in jobs:
+            a = self.vols[v1][m1[2]:m1[2] + d[2], m1[1]:m1[1] + d[1], m1[0]:m1[0] + d[0]]
+            b = self.vols[v2][m2[2]:m2[2] + d[2], m2[1]:m2[1] + d[1], m2[0]:m2[0] + d[0]]
+            out.append(self.pcm_pair(np.ascontiguousarray(a), np.ascontiguousarray(b), p))
+        return out
+
     # -- volumes
     def volume_upload(self, vol):
         h = self.next
@@ -46,10 +54,16 @@ class FakeContext:
     def volume_free(self, h):
         del self.vols[h]
 
-    def volume_download(self, h, dims_xyz, dtype=np.float32):
+    def volume_download(self, h, dims_xyz=None, dtype=None):
         v = self.vols[h]
-        assert tuple(v.shape[::-1]) == tuple(int(d) for d in dims_xyz) and v.dtype == np.dtype(dtype)
+        if dims_xyz is not None:
+            assert tuple(v.shape[::-1]) == tuple(int(d) for d in dims_xyz)
+        if dtype is not None:
+            assert v.dtype == np.dtype(dtype)
         return v.copy()
+
+    def content_weights(self, h, sigma1=20.0, sigma2=40.0):
+        return self.volume_upload(fo.content_weights(self.vols[h], sigma1, sigma2))
 
     def downsample(self, h, factors):
         self.calls["downsample"] += 1
@@ -64,8 +78,18 @@ class FakeContext:
     def _views(self, views):
         out = []
         for v in views:
-            out.append(fo.View(self.vols[v["vol_handle"]], np.asarray(v["src_to_world"], dtype=np.float64).reshape(3, 4),
-                               v.get("blend_border", (0, 0, 0)), v.get("blend_range", (40, 40, 40))))
+            vol = self.vols[v["vol_handle"]]
+            fd = tuple(int(x) for x in v.get("full_dims", (0, 0, 0)))
+            if fd[0] > 0:   # windowed view: the resident array is the sub-interval [window_min, +shape) of the view
+                w = tuple(int(x) for x in v.get("window_min", (0, 0, 0)))
+                full = np.zeros(fd[::-1], dtype=vol.dtype)
+                z, y, x = vol.shape
+                full[w[2]:w[2] + z, w[1]:w[1] + y, w[0]:w[0] + x] = vol
+                vol = full
+            c = v.get("content_handle", 0)
+            out.append(fo.View(vol, np.asarray(v["src_to_world"], dtype=np.float64).reshape(3, 4),
+                               v.get("blend_border", (0, 0, 0)), v.get("blend_range", (40, 40, 40)),
+                               self.vols[c] if c else None))
         return out
 
     def fuse_block(self, views, block_min, block_size, params=None, out=None):
@@ -76,6 +100,14 @@ class FakeContext:
         if out is not None:
             out[...] = res
             return out
+        return res
+
+    def fuse_blocks(self, views, block_mins, block_sizes, params=None, outs=None):
+        res = [self.fuse_block(views, mn, sz, params) for mn, sz in zip(block_mins, block_sizes)]
+        if outs is not None:
+            for o, r in zip(outs, res):
+                o[...] = r
+            return outs
         return res
 
     def fuse_block_to_volume(self, views, block_min, block_size, params=None):

@@ -34,7 +34,7 @@ def test_stitching_then_fusion_end_to_end(ctx, tmp_path):
     commands.create_fusion_container(xml, out, block_size=(32, 32, 32))
     ds = commands.affine_fusion(out, ctx, "AVG_BLEND", block_scale=(2, 2, 1))
     st, meta = bn5.read_fusion_container(out)
-    fused = st.read_volume(ds)
+    fused = st.read_volume(ds[0])
     assert meta["bb_min"] == [0, 0, 0] and meta["bb_max"] == [nominal + n - 1, n - 1, n - 1]
     views = []
     for vol, t in ((A, (0, 0, 0)), (B, (nominal, 0, 0))):
@@ -64,7 +64,7 @@ def test_stitching_then_fusion_end_to_end(ctx, tmp_path):
     commands.create_fusion_container(xml, outz, block_size=(32, 32, 32))
     dz = commands.affine_fusion(outz, ctx, "AVG_BLEND", block_scale=(2, 2, 1))
     stz, mz = bz.read_fusion_container_zarr(outz)
-    assert mz["format"] == "OME-ZARR" and dz == "0"
+    assert mz["format"] == "OME-ZARR" and dz == ["0"]
     assert np.array_equal(stz.read_volume("0"), fused)
 
 
