@@ -54,6 +54,17 @@ class ViewC(C.Structure):
                 ("blend_range", C.c_float * 3), ("full_dims", C.c_longlong * 3), ("window_min", C.c_longlong * 3)]
 
 
+class DogParamsC(C.Structure):
+    _fields_ = [("sigma", C.c_double), ("threshold", C.c_double), ("min_intensity", C.c_double),
+                ("max_intensity", C.c_double), ("find_max", C.c_int), ("find_min", C.c_int),
+                ("localization", C.c_int), ("pad", C.c_int)]
+
+
+class DogPointC(C.Structure):
+    _fields_ = [("loc", C.c_double * 3), ("value", C.c_double), ("voxel", C.c_longlong * 3), ("is_max", C.c_int),
+                ("pad", C.c_int)]
+
+
 class PcmJobC(C.Structure):
     _fields_ = [("vol1", C.c_ulonglong), ("vol2", C.c_ulonglong), ("min1", C.c_longlong * 3),
                 ("min2", C.c_longlong * 3), ("dims", C.c_longlong * 3)]
@@ -87,7 +98,7 @@ SYMBOLS = [
     "bs_pcm_default_params", "bs_pcm_pair", "bs_pcm_batch", "bs_pcm_volumes_batch", "bs_good_fft_size", "bs_pcm_debug_pcm",
     "bs_fuse_default_params", "bs_volume_upload", "bs_volume_upload_async", "bs_volume_wrap", "bs_volume_free",
     "bs_content_weights", "bs_volume_info", "bs_volume_download", "bs_volume_devptr", "bs_downsample", "bs_fuse_block", "bs_fuse_blocks",
-    "bs_fuse_block_to_volume", "bs_fuse_accumulate", "bs_fuse_finish",
+    "bs_fuse_block_to_volume", "bs_fuse_accumulate", "bs_fuse_finish", "bs_dog_default_params", "bs_dog_detect",
 ]
 
 
@@ -140,6 +151,9 @@ def load_library():
     lib.bs_fuse_block_to_volume.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), P(ull)]
     lib.bs_fuse_accumulate.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), vp, vp]
     lib.bs_fuse_finish.argtypes = [vp, vp, vp, ll, P(FuseParamsC), vp, ip]
+    lib.bs_dog_default_params.argtypes = [P(DogParamsC)]
+    lib.bs_dog_default_params.restype = None
+    lib.bs_dog_detect.argtypes = [vp, ull, P(ll), P(ll), P(DogParamsC), P(DogPointC), ip, P(ip)]
     _lib = lib
     return lib
 
@@ -369,6 +383,24 @@ class Context:
         out = np.empty(dims[::-1], dtype=dt)
         self._check(self.lib.bs_volume_download(self.h, handle, out.ctypes.data, out.nbytes))
         return out
+
+    # -- next row: DoG interest points
+    def dog_detect(self, handle: int, interval_min_xyz, interval_size_xyz, sigma=1.8, threshold=0.008, min_intensity=0.0,
+                   max_intensity=65535.0, find_max=True, find_min=False, localization=True, max_points=1 << 16):
+        """DoG detections of one block of a resident view: list of (loc_xyz, value, voxel_xyz, is_max) sorted by
+        (z, y, x).  The buffer grows until every detection fits."""
+        p = DogParamsC(float(sigma), float(threshold), float(min_intensity), float(max_intensity),
+                       1 if find_max else 0, 1 if find_min else 0, 1 if localization else 0, 0)
+        mn = (C.c_longlong * 3)(*[int(v) for v in interval_min_xyz])
+        sz = (C.c_longlong * 3)(*[int(v) for v in interval_size_xyz])
+        while True:
+            buf = (DogPointC * max(1, max_points))()
+            n = C.c_int()
+            self._check(self.lib.bs_dog_detect(self.h, handle, mn, sz, C.byref(p), buf, max_points, C.byref(n)))
+            if n.value <= max_points:
+                break
+            max_points = n.value
+        return [(tuple(buf[i].loc), buf[i].value, tuple(buf[i].voxel), bool(buf[i].is_max)) for i in range(n.value)]
 
     @staticmethod
     def fuse_params(fusion_type=FUSE_AVG_BLEND, interpolation=1, out_dtype=DTYPE_F32, blend_lut_n=0,

@@ -222,6 +222,35 @@ int bs_fuse_accumulate(bs_ctx* ctx, const bs_view* views, int n_views, const lon
 int bs_fuse_finish(bs_ctx* ctx, const float* sum_wi_dev, const float* sum_w_dev, long long n,
                    const bs_fuse_params* params, void* out, int out_on_device);
 
+/* ---------------------------------------------------------------- next row: DoG interest points
+ * DoGImgLib2.computeDoG on one block of a resident view (J/SparkInterestPointDetection.java:469-566; the reference
+ * passes dog.cuda = null at :490-493 -- this is the device implementation behind that hook).  The caller walks the
+ * reference's block grid and expands every block by one voxel inside the image (:397-424). */
+typedef struct {
+    double sigma;           /* -s, e.g. 1.8 */
+    double threshold;       /* -t, e.g. 0.008 */
+    double min_intensity;   /* -i0 */
+    double max_intensity;   /* -i1 */
+    int    find_max;        /* --type MAX / BOTH */
+    int    find_min;        /* --type MIN / BOTH */
+    int    localization;    /* 0 NONE, 1 QUADRATIC */
+    int    pad;
+} bs_dog_params;
+
+typedef struct {
+    double    loc[3];       /* sub-pixel location {x,y,z} in the view's pixel coordinates */
+    double    value;        /* (interpolated) DoG value */
+    long long voxel[3];     /* integer location of the extremum */
+    int       is_max;
+    int       pad;
+} bs_dog_point;
+
+void bs_dog_default_params(bs_dog_params* p);
+/* detections of the block [interval_min, interval_min + interval_size) sorted by (z, y, x); *n_found may exceed
+ * max_points (buffer too small: only max_points were written) */
+int bs_dog_detect(bs_ctx* ctx, unsigned long long vol_handle, const long long interval_min[3], const long long interval_size[3],
+                  const bs_dog_params* params, bs_dog_point* out, int max_points, int* n_found);
+
 #ifdef __cplusplus
 }
 #endif
