@@ -50,9 +50,12 @@ __global__ void __launch_bounds__(GA_THREADS) k_gauss_x(const __grid_constant__ 
     for (int i = threadIdx.x; i < nl * len; i += blockDim.x) {
         const int l = i / len, x = i - l * len;
         const float* b = buf + l * w + x;
-        float s = 0.f;
-        for (int t = 0; t <= 2 * r; ++t) s = fmaf(kt[t], b[t], s);
-        a.out[(row0 + l) * len + x] = s;
+        // double accumulation: with the default sigmas 20 / 40 a line sums 123 / 243 taps and the second blur works
+        // on squared differences -- fp32 running sums miss the 1e-4 bar of the fused result (off the hot path: the
+        // content volume is computed once per view)
+        double s = 0.0;
+        for (int t = 0; t <= 2 * r; ++t) s = fma((double)kt[t], (double)b[t], s);
+        a.out[(row0 + l) * len + x] = (float)s;
     }
 }
 
@@ -75,9 +78,9 @@ __global__ void __launch_bounds__(GA_THREADS) k_gauss_strided(const __grid_const
     if (!ok) return;
     for (int o = wy; o < len; o += nwy) {
         const float* b = buf + o * 32 + lane;
-        float s = 0.f;
-        for (int t = 0; t <= 2 * r; ++t) s = fmaf(kt[t], b[t * 32], s);
-        a.out[base + (long long)o * stride] = s;
+        double s = 0.0;
+        for (int t = 0; t <= 2 * r; ++t) s = fma((double)kt[t], (double)b[t * 32], s);
+        a.out[base + (long long)o * stride] = (float)s;
     }
 }
 

@@ -30,7 +30,7 @@ def _scene(seed=0, n=3, shape=(40, 48, 56), dtype=np.uint16, rot=0.0, jitter=Tru
 
 
 def _run(ctx, views, bmin, bsize, fusion_type, out_dtype="float32", interpolation=1, lut=0,
-         min_i=0.0, max_i=65535.0, contents=None):
+         min_i=0.0, max_i=65535.0, contents=None, content_sigmas=(2.0, 4.0)):
     import bsgpu
     nat = bsgpu.native
     handles = [ctx.volume_upload(v) for v, _ in views]
@@ -41,8 +41,8 @@ def _run(ctx, views, bmin, bsize, fusion_type, out_dtype="float32", interpolatio
         border, rng = fo.adjust_blending(M)
         c = None
         if fusion_type in (fo.AVG_CONTENT, fo.AVG_BLEND_CONTENT):
-            chandles[i] = ctx.content_weights(handles[i], 2.0, 4.0)
-            c = fo.content_weights(vol, 2.0, 4.0)
+            chandles[i] = ctx.content_weights(handles[i], *content_sigmas)
+            c = fo.content_weights(vol, *content_sigmas)
         ov.append(fo.View(vol, M, border, rng, c))
         gv.append(dict(src_to_world=M, vol_handle=handles[i], content_handle=chandles[i],
                        blend_border=border, blend_range=rng))
@@ -123,10 +123,11 @@ def test_avg_blend_anisotropic_scale(ctx):
 
 
 @pytest.mark.parametrize("ft", [fo.AVG_CONTENT, fo.AVG_BLEND_CONTENT])
-def test_content_based(ctx, ft):
+@pytest.mark.parametrize("sigmas", [(2.0, 4.0), (20.0, 40.0)])      # small, and upstream's defaults (north_star bar 1e-4)
+def test_content_based(ctx, ft, sigmas):
     views = _scene(seed=4, n=2)
-    got, want = _run(ctx, views, (0, 0, 0), (100, 50, 40), ft)
-    _assert_close(got, want, rtol=5e-4)  # Gaussian sums accumulate in fp32 on the device, fp64 in scipy
+    got, want = _run(ctx, views, (0, 0, 0), (100, 50, 40), ft, content_sigmas=sigmas)
+    _assert_close(got, want)
 
 
 def test_content_weight_volume(ctx):
