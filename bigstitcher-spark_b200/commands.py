@@ -29,17 +29,23 @@ def _load_views(data: SpimData2, store: bn5.N5Store, view_ids, level=0):
 
 def stitching(xml_path, ctx: Context, downsampling=(2, 2, 1), peaks_to_check=5, disable_subpixel=False,
               min_r=0.3, max_r=1.0, max_shift_xyz=None, max_shift_total=None, dry_run=False,
-              channel_combine="AVERAGE", illum_combine="PICK_BRIGHTEST"):
+              channel_combine="AVERAGE", illum_combine="PICK_BRIGHTEST", shard=(0, 1), allgather=None):
     """`./stitching -x dataset.xml [-ds 2,2,1] [-p 5] [--channelCombine AVERAGE] [--illumCombine PICK_BRIGHTEST] ...`:
     phase-correlate every overlapping pair of tile GROUPS (a tile's channels / illuminations are combined,
     J/SparkPairwiseStitching.java:103-107,141-165,204-208) and store the filtered results in the XML's
-    <StitchingResults>.  Returns all raw results."""
+    <StitchingResults>.  Returns all raw results.
+
+    Multi-GPU (SURVEY 8e): pairs are independent, so rank r of w takes pairs[r::w] (``shard``) with no data-path
+    collective; ``allgather(obj) -> [obj of every rank]`` (e.g. torch.distributed.all_gather_object) merges the
+    20-doubles-per-pair results and rank 0 writes the XML."""
     data = SpimData2.load(xml_path)
     fmt, n5_path = data.image_loader()
     if fmt != "bdv.n5":
         raise NotImplementedError(f"ImageLoader format {fmt}")
     store = bn5.N5Store(n5_path)
-    pairs = data.stitching_groups()
+    all_pairs = data.stitching_groups()
+    rank, world = shard
+    pairs = all_pairs[rank::world]
     needed = sorted({v for p in pairs for g in p for v in g})
     tiles = _load_views(data, store, needed)
     models = {v: data.model(*v) for v in needed}
@@ -50,6 +56,14 @@ def stitching(xml_path, ctx: Context, downsampling=(2, 2, 1), peaks_to_check=5, 
     for (ga, gb), r in zip(pairs, raw):
         if r is not None:   # hash of the FIRST views' registrations (J/SparkPairwiseStitching.java:287-289)
             r.hash = SpimData2.transform_hash(data.registrations[ga[0]], data.registrations[gb[0]])
+    if world > 1:
+        parts = allgather(raw)
+        merged = [None] * len(all_pairs)
+        for r_, part in enumerate(parts):
+            merged[r_::world] = part
+        raw, pairs = merged, all_pairs
+        if rank != 0:
+            return raw
     # every compared pair loses its stored result (a->b and b->a), found or not (:323-325); then the new ones go in
     data.remove_stitching_results(pairs)
     kept = bst.filter_results(raw, min_r, max_r, max_shift_xyz, max_shift_total)
@@ -184,7 +198,7 @@ def _source_window(src_to_world, level_dims, wmin, wmax, margin=3):
 
 
 def affine_fusion(out_path, ctx: Context, fusion_type="AVG_BLEND", block_scale=(2, 2, 1), channel=None, timepoint=None,
-                  retries=5, blocks_per_call=16, interpolation=1):
+                  retries=5, blocks_per_call=16, interpolation=1, shard=(0, 1), barrier=None):
     """`./affine-fusion -o fused.zarr [-f AVG_BLEND] [--blockScale 2,2,1] [-c channelIndex] [-t timepointIndex]`:
     read the container metadata and, for every (channel, timepoint) volume (J/SparkAffineFusion.java:425-440), fuse
     its views super-block by super-block on the device, write the blocks with N5Utils.saveBlock semantics and build
@@ -193,7 +207,10 @@ def affine_fusion(out_path, ctx: Context, fusion_type="AVG_BLEND", block_scale=(
     Source staging is block-wise (OverlappingBlocks / ViewUtil.findOverlappingBlocks, J/fusion/OverlappingBlocks.java:
     133-161): the super-block grid is walked in z-slabs; for every slab only the source WINDOW of each overlapping
     view is read from its container -- at the mipmap level ViewUtil's best-resolution rule picks
-    (J/util/ViewUtil.java:425-493) -- uploaded as a windowed view and freed after the slab."""
+    (J/util/ViewUtil.java:425-493) -- uploaded as a windowed view and freed after the slab.
+
+    Multi-GPU ("one N5 block-grid slab per device"): rank r of w (``shard``) fuses a contiguous run of
+    z-slabs, no data-path collective; ``barrier()`` separates s0 from the pyramid levels that re-read it."""
     is_zarr = os.path.exists(os.path.join(out_path, ".zgroup"))
     store, meta = (bzarr.read_fusion_container_zarr if is_zarr else bn5.read_fusion_container)(out_path)
     data = SpimData2.load(meta["input_xml"])
@@ -216,13 +233,13 @@ def affine_fusion(out_path, ctx: Context, fusion_type="AVG_BLEND", block_scale=(
             done.add((ci, ti))
             levels = meta["mr_infos"][0 if is_zarr else ci + ti * nc]
             _fuse_volume_blockwise(ctx, data, src, _Sink(store, is_zarr, ci, ti), meta, levels, data.views_of(ci, ti),
-                                   fusion_type, interpolation, block_scale, retries, blocks_per_call)
+                                   fusion_type, interpolation, block_scale, retries, blocks_per_call, shard, barrier)
             written.append(levels[0]["dataset"])
     return written
 
 
 def _fuse_volume_blockwise(ctx, data, src, sink, meta, levels, view_ids, fusion_type, interpolation, block_scale,
-                           retries, blocks_per_call):
+                           retries, blocks_per_call, shard=(0, 1), barrier=None):
     af = meta["anisotropy_factor"] if meta["preserve_anisotropy"] else float("nan")
     regs = bf.adjust_all_transforms({v: data.model(*v) for v in view_ids}, af)
     bb_min = np.asarray(meta["bb_min"], dtype=np.int64)
@@ -258,9 +275,13 @@ def _fuse_volume_blockwise(ctx, data, src, sink, meta, levels, view_ids, fusion_
     slabs = {}
     for gb in grid:
         slabs.setdefault(gb[0][2], []).append(gb)
+    rank, world = shard
+    zs = sorted(slabs)
+    per = -(-len(zs) // world)
+    my_z = zs[rank * per:(rank + 1) * per]           # contiguous run of z-slabs per device
     whole = {}      # fallback residency (content weights, winner types, float sources ...): whole views, kept
     try:
-        for z0 in sorted(slabs):
+        for z0 in my_z:
             blocks = slabs[z0]
             lo = bb_min + np.array([0, 0, z0])
             hi = bb_min + np.array([dims[0] - 1, dims[1] - 1, min(dims[2], z0 + compute[2]) - 1])
@@ -324,10 +345,12 @@ def _fuse_volume_blockwise(ctx, data, src, sink, meta, levels, view_ids, fusion_
     # the 2x average of its region of level l-1 (N5ApiTools.writeDownsampledBlock[5dOMEZARR]), read back from the
     # container and averaged on the device (bs_downsample)
     for li in range(1, 1 if fast_pyramid else len(levels)):
+        if barrier is not None:
+            barrier()                                # level l-1 is complete on every rank
         prev, cur = levels[li - 1], levels[li]
         rel = [int(v) for v in cur["relativeDownsampling"][:3]]
         cdims = [int(v) for v in cur["dimensions"][:3]]
-        todo, attempt = bf.grid_create(cdims, compute, bs), 0
+        todo, attempt = bf.grid_create(cdims, compute, bs)[rank::world], 0
         while todo:
             attempt += 1
             if attempt > retries:

@@ -76,3 +76,63 @@ def test_view_sharded_allreduce_gloo_world2():
     assert err.max() < 1e-5           # float re-association only
     assert [p for p, _ in allres] == [(i, i + 1) for i in range(7)]
     assert [r for _, r in allres] == [0, 0, 0, 0, 1, 1, 1]
+
+
+def _cmd_worker(rank, world, port, tmp, q):
+    """The command bodies sharded over two gloo ranks (oracle-backed fake context): pairs[r::w] + all_gather_object for
+    `stitching`, contiguous z-slabs + barrier for `affine-fusion` with a re-read pyramid."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from bsgpu import commands
+    from tests.fake_ctx import FakeContext
+
+    def allgather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+    ctx = FakeContext()
+    xml = os.path.join(tmp, "dataset.xml")
+    raw = commands.stitching(xml, ctx, downsampling=(1, 1, 1), shard=(rank, world), allgather=allgather)
+    dist.barrier()
+    out = os.path.join(tmp, "fused.n5")
+    commands.affine_fusion(out, ctx, "AVG_BLEND", block_scale=(1, 1, 1), shard=(rank, world), barrier=dist.barrier)
+    dist.barrier()
+    if rank == 0:
+        q.put(([None if r is None else (r.pair, np.rint(r.transform[:, 3]).tolist()) for r in raw], ctx.calls["pcm"]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_commands_gloo_world2(tmp_path):
+    from bsgpu import commands, n5 as bn5, spimdata
+    from tests.test_commands_cpu import _dataset
+    xml, vols, tiles, planted, nominal = _dataset(tmp_path)
+    out = str(tmp_path / "fused.n5")
+    commands.create_fusion_container(xml, out, block_size=(16, 16, 16), downsamplings=[(2, 2, 1)], compression="raw")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_cmd_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    raw, npcm0 = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert len(raw) == 3 and npcm0 == 2                       # rank 0 correlated pairs 0 and 2, rank 1 pair 1
+    assert raw[0][1] == list(planted[1]) and raw[1][1] == list(planted[2])
+    assert len(spimdata.SpimData2.load(xml).stitching_results()) == 3
+    views = []
+    for t in tiles:
+        M = synth.translation(t["translation_xyz"])
+        border, rng = fo.adjust_blending(M)
+        views.append(fo.View(vols[t["setup"]], M, border, rng))
+    ext = (nominal + 48, nominal + 48, 48)
+    want = fo.fuse_block(views, (0, 0, 0), ext, fo.AVG_BLEND)
+    st, _ = bn5.read_fusion_container(out)
+    assert np.array_equal(st.read_volume("ch0tp0/s0"), want)              # two ranks, three z-slabs, no seam
+    assert np.array_equal(st.read_volume("ch0tp0/s1"), fo.downsample2x(want, (2, 2, 1)))

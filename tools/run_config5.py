@@ -1,0 +1,134 @@
+#!/usr/bin/env python
+"""BASELINE configs[4] shape at a chosen size: synthetic lightsheet grid (uint16 tiles, ~10 % overlap, planted jitter
+<= 5 px) written as SpimData2 XML + BDV-N5 (raw) on tmpfs, then `stitching` + `create-fusion-container` +
+`affine-fusion` end to end through the command bodies, sharded over the ranks of one box.
+
+    python tools/run_config5.py --grid 4x4x2 --tile 256x256x128 [--ds 1,1,1] [--workdir /dev/shm/bs_cfg5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 tools/run_config5.py ...
+
+Prints one JSON line (rank 0): pairs/s of the stitching stage and fused Mvoxels/s of the fusion stage, both WITH
+container I/O (N5 raw on tmpfs -> N5 raw on tmpfs), the quantities SURVEY 8(d) config 5 names."""
+import argparse
+import json
+import os
+import shutil
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grid", default="4x4x2")
+    ap.add_argument("--tile", default="256x256x128")
+    ap.add_argument("--overlap", type=float, default=0.10)
+    ap.add_argument("--ds", default="1,1,1")
+    ap.add_argument("--workdir", default="/dev/shm/bs_cfg5")
+    ap.add_argument("--keep", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch
+    import torch.distributed as dist
+    import bsgpu
+    from bsgpu import commands, n5 as bn5, spimdata, synthetic
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    g = [int(v) for v in args.grid.split("x")]
+    t = [int(v) for v in args.tile.split("x")]
+    ds = tuple(int(v) for v in args.ds.split(","))
+    stride = [int(round(t[d] * (1 - args.overlap))) for d in range(3)]
+    rng = np.random.default_rng(9)
+    xml = os.path.join(args.workdir, "dataset.xml")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allgather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    # ---- dataset (rank 0 writes the XML; tiles are written by all ranks round-robin)
+    tiles = []
+    idx = 0
+    for k in range(g[2]):
+        for j in range(g[1]):
+            for i in range(g[0]):
+                nominal = (i * stride[0], j * stride[1], k * stride[2])
+                jit = tuple(int(v) for v in rng.integers(-5, 6, 3))
+                tiles.append(dict(setup=idx, size_xyz=tuple(t), tile=idx, translation_xyz=nominal, jitter=jit))
+                idx += 1
+    if rank == 0:
+        shutil.rmtree(args.workdir, ignore_errors=True)
+        os.makedirs(args.workdir)
+    barrier()
+    store = bn5.N5Store(os.path.join(args.workdir, "dataset.n5"), create=True)
+    ext = [stride[d] * (g[d] - 1) + t[d] + 16 for d in range(3)]
+    t0 = time.perf_counter()
+    fld = synthetic.smooth_field((ext[2], ext[1], ext[0]), 9000, dev) if len(tiles) else None
+    for tl in tiles[rank::world]:
+        o = [8 + tl["translation_xyz"][d] + tl["jitter"][d] for d in range(3)]
+        vol = synthetic.tile_from_field(fld, (o[2], o[1], o[0]), (t[2], t[1], t[0]), 9100 + tl["setup"]).cpu().numpy().view(np.uint16)
+        bn5.write_bdv_setup(store, tl["setup"], 0, vol, (128, 128, 64), compression="raw")
+    del fld
+    torch.cuda.empty_cache()
+    if rank == 0:
+        spimdata.write_dataset_xml(xml, "dataset.n5", tiles)
+    barrier()
+    t_data = time.perf_counter() - t0
+
+    ctx = bsgpu.Context(local)
+    # ---- stitching
+    barrier()
+    t0 = time.perf_counter()
+    raw = commands.stitching(xml, ctx, downsampling=ds, shard=(rank, world), allgather=allgather if world > 1 else None)
+    barrier()
+    t_st = time.perf_counter() - t0
+    npairs = len(raw)
+    ok = 0
+    if rank == 0:
+        by_setup = {tl["setup"]: tl for tl in tiles}
+        for r in raw:
+            if r is None:
+                continue
+            (a, b) = r.pair
+            want = np.subtract(by_setup[b[1]]["jitter"], by_setup[a[1]]["jitter"])
+            ok += int(np.all(np.abs(np.asarray(r.transform)[:, 3] - want) < 0.75))
+    # ---- fusion
+    out = os.path.join(args.workdir, "fused.n5")
+    if rank == 0:
+        commands.create_fusion_container(xml, out, block_size=(128, 128, 64), dtype="uint16", compression="raw", storage="N5")
+    barrier()
+    t0 = time.perf_counter()
+    commands.affine_fusion(out, ctx, "AVG_BLEND", block_scale=(2, 2, 2), shard=(rank, world), barrier=barrier, blocks_per_call=32)
+    barrier()
+    t_fu = time.perf_counter() - t0
+    if rank == 0:
+        _, meta = bn5.read_fusion_container(out)
+        dims = [meta["bb_max"][d] - meta["bb_min"][d] + 1 for d in range(3)]
+        nvox = int(np.prod(dims))
+        print(json.dumps({"config": f"BASELINE configs[4] shape: {args.grid} grid of {args.tile} uint16 tiles, {int(args.overlap * 100)} % overlap, "
+                                    f"jitter <= 5 px, N5 raw on {args.workdir}", "n_gpus": world, "tiles": len(tiles),
+                          "stitching": {"pairs": npairs, "seconds": round(t_st, 3), "pairs_per_s": round(npairs / t_st, 2), "ds": list(ds),
+                                        "planted_jitter_recovered": f"{ok}/{sum(r is not None for r in raw)}"},
+                          "fusion": {"dims": dims, "seconds": round(t_fu, 3), "mvoxels_per_s": round(nvox / t_fu / 1e6, 1), "dtype": "uint16"},
+                          "dataset_write_s": round(t_data, 2), "launches": ctx.launch_count()}), flush=True)
+    ctx.close()
+    barrier()
+    if rank == 0 and not args.keep:
+        shutil.rmtree(args.workdir, ignore_errors=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
