@@ -99,6 +99,7 @@ SYMBOLS = [
     "bs_fuse_default_params", "bs_volume_upload", "bs_volume_upload_async", "bs_volume_wrap", "bs_volume_free",
     "bs_content_weights", "bs_volume_info", "bs_volume_download", "bs_volume_devptr", "bs_downsample", "bs_fuse_block", "bs_fuse_blocks",
     "bs_fuse_block_to_volume", "bs_fuse_accumulate", "bs_fuse_finish", "bs_dog_default_params", "bs_dog_detect",
+    "bs_comm_unique_id", "bs_comm_init", "bs_comm_destroy", "bs_fuse_allreduce",
 ]
 
 
@@ -151,6 +152,10 @@ def load_library():
     lib.bs_fuse_block_to_volume.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), P(ull)]
     lib.bs_fuse_accumulate.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), vp, vp]
     lib.bs_fuse_finish.argtypes = [vp, vp, vp, ll, P(FuseParamsC), vp, ip]
+    lib.bs_comm_unique_id.argtypes = [C.c_char_p]
+    lib.bs_comm_init.argtypes = [vp, ip, ip, C.c_char_p]
+    lib.bs_comm_destroy.argtypes = [vp]
+    lib.bs_fuse_allreduce.argtypes = [vp, vp, vp, ll]
     lib.bs_dog_default_params.argtypes = [P(DogParamsC)]
     lib.bs_dog_default_params.restype = None
     lib.bs_dog_detect.argtypes = [vp, ull, P(ll), P(ll), P(DogParamsC), P(DogPointC), ip, P(ip)]
@@ -488,6 +493,30 @@ class Context:
         if not (d1 and d2):
             raise ValueError("accumulators must be device buffers")
         self._check(self.lib.bs_fuse_accumulate(self.h, arr, n, bmin, bsz, C.byref(params), p1, p2))
+
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """rank 0: a fresh 128-byte NCCL id to hand to every rank (any host channel)."""
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.bs_comm_unique_id(buf)
+        if rc != 0:
+            raise BsError(rc, lib.bs_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, n_ranks: int, rank: int, unique_id: bytes):
+        self._check(self.lib.bs_comm_init(self.h, int(n_ranks), int(rank), unique_id))
+
+    def comm_destroy(self):
+        self._check(self.lib.bs_comm_destroy(self.h))
+
+    def fuse_allreduce(self, sum_wi, sum_w, n_elems):
+        """In-place SUM of both partial buffers over the ranks of bs_comm_init (NCCL, on this context's stream)."""
+        p1, d1, _ = _ptr_of(sum_wi)
+        p2, d2, _ = _ptr_of(sum_w)
+        if not (d1 and d2):
+            raise ValueError("accumulators must be device buffers")
+        self._check(self.lib.bs_fuse_allreduce(self.h, p1, p2, int(n_elems)))
 
     def fuse_finish(self, sum_wi, sum_w, n_elems, params, out):
         p1, _, _ = _ptr_of(sum_wi)

@@ -46,6 +46,34 @@ def allreduce_partials(sum_wi, sum_w, group=None):
     return sum_wi, sum_w
 
 
+def comm_init_from_torch(ctx, group=None):
+    """Join the library's NCCL communicator: rank 0 draws the id (bs_comm_unique_id), torch.distributed carries the 128
+    bytes to the other ranks (host plumbing), every rank calls bs_comm_init."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    box = [ctx.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    ctx.comm_init(world, rank, box[0])
+
+
+def fuse_block_view_sharded_native(ctx, my_views, block_min, block_size, params, out=None):
+    """View-sharded fusion with the exchange INSIDE the library: bs_fuse_accumulate -> bs_fuse_allreduce (one grouped
+    NCCL all-reduce on the context's stream) -> bs_fuse_finish, no host synchronisation in between."""
+    import numpy as np
+    import torch
+    n = int(block_size[0]) * int(block_size[1]) * int(block_size[2])
+    dev = torch.device("cuda", ctx.device)
+    swi = torch.zeros(n, dtype=torch.float32, device=dev)
+    sw = torch.zeros(n, dtype=torch.float32, device=dev)
+    torch.cuda.synchronize(dev)
+    ctx.fuse_accumulate(my_views, block_min, block_size, params, swi, sw)
+    ctx.fuse_allreduce(swi, sw, n)
+    if out is None:
+        from . import native
+        out = np.empty(tuple(int(v) for v in block_size)[::-1], dtype=native._BS2NP[params.out_dtype])
+    return ctx.fuse_finish(swi, sw, n, params, out)
+
+
 def fuse_block_view_sharded(ctx, my_views, block_min, block_size, params, out=None, group=None):
     """View-sharded fusion of one block on the GPU: accumulate this rank's views, all-reduce the two
     partial-sum buffers, finish (divide + convert).  Every rank ends up with the full block."""

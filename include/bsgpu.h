@@ -221,6 +221,14 @@ int bs_fuse_accumulate(bs_ctx* ctx, const bs_view* views, int n_views, const lon
                        float* sum_wi_dev, float* sum_w_dev);
 int bs_fuse_finish(bs_ctx* ctx, const float* sum_wi_dev, const float* sum_w_dev, long long n,
                    const bs_fuse_params* params, void* out, int out_on_device);
+/* The exchange itself, inside the library: rank 0 draws a 128-byte NCCL id (bs_comm_unique_id) and hands it to the
+ * other ranks by any host channel (the Spark driver / torch.distributed store); every rank joins with bs_comm_init;
+ * bs_fuse_allreduce sums both partial buffers of the (overlap) region over all ranks in place -- one grouped NCCL
+ * all-reduce over NVLink / NVSwitch, queued on the context's stream between bs_fuse_accumulate and bs_fuse_finish. */
+int bs_comm_unique_id(unsigned char id[128]);
+int bs_comm_init(bs_ctx* ctx, int n_ranks, int rank, const unsigned char id[128]);
+int bs_comm_destroy(bs_ctx* ctx);
+int bs_fuse_allreduce(bs_ctx* ctx, float* sum_wi_dev, float* sum_w_dev, long long n);
 
 /* ---------------------------------------------------------------- next row: DoG interest points
  * DoGImgLib2.computeDoG on one block of a resident view (J/SparkInterestPointDetection.java:469-566; the reference

@@ -385,6 +385,31 @@ JF(void, fuseFinish)(JNIEnv* env, jclass, jlong ctx, jlong sumWiDev, jlong sumWD
     failed(env, ctx, rc);
 }
 
+// the exchange behind the C ABI: rank 0 draws the id, the Java driver ships the 128 bytes, every worker joins
+JF(jbyteArray, commUniqueId)(JNIEnv* env, jclass) {
+    unsigned char id[128];
+    if (bs_comm_unique_id(id) != BS_OK) {
+        jclass ex = env->FindClass("java/lang/RuntimeException");
+        if (ex) env->ThrowNew(ex, bs_last_error(nullptr));
+        return nullptr;
+    }
+    jbyteArray a = env->NewByteArray(128);
+    env->SetByteArrayRegion(a, 0, 128, reinterpret_cast<const jbyte*>(id));
+    return a;
+}
+
+JF(void, commInit)(JNIEnv* env, jclass, jlong ctx, jint nRanks, jint rank, jbyteArray id) {
+    jbyte b[128];
+    env->GetByteArrayRegion(id, 0, 128, b);
+    failed(env, ctx, bs_comm_init(C(ctx), nRanks, rank, reinterpret_cast<const unsigned char*>(b)));
+}
+
+JF(void, commDestroy)(JNIEnv* env, jclass, jlong ctx) { failed(env, ctx, bs_comm_destroy(C(ctx))); }
+
+JF(void, fuseAllreduce)(JNIEnv* env, jclass, jlong ctx, jlong sumWiDev, jlong sumWDev, jlong n) {
+    failed(env, ctx, bs_fuse_allreduce(C(ctx), reinterpret_cast<float*>(sumWiDev), reinterpret_cast<float*>(sumWDev), n));
+}
+
 // ---------------------------------------------------------------------------------------- next row: DoG
 // returns n * 8 doubles {locX, locY, locZ, value, voxelX, voxelY, voxelZ, isMax}
 JF(jdoubleArray, dogDetect)(JNIEnv* env, jclass, jlong ctx, jlong handle, jlongArray intervalMin, jlongArray intervalSize,

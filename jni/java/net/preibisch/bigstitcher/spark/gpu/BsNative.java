@@ -64,6 +64,11 @@ public final class BsNative
 			long[] blockMin, long[] blockSize, int[] iparams, double[] dparams );
 	public static native void fuseAccumulate( long ctx, int nViews, double[] models, long[] handles, float[] blend,
 			long[] blockMin, long[] blockSize, int[] iparams, double[] dparams, long sumWiDev, long sumWDev );
+	/** view-sharded exchange: rank 0 draws the id, every rank joins, fuseAllreduce sums both partial buffers over NVLink */
+	public static native byte[] commUniqueId();
+	public static native void commInit( long ctx, int nRanks, int rank, byte[] id );
+	public static native void commDestroy( long ctx );
+	public static native void fuseAllreduce( long ctx, long sumWiDev, long sumWDev, long n );
 	public static native void fuseFinish( long ctx, long sumWiDev, long sumWDev, long n, int[] iparams, double[] dparams, Object dest );
 
 	/** n x {locX, locY, locZ, value, voxelX, voxelY, voxelZ, isMax}; dparams {sigma, threshold, minI, maxI}; iparams {findMax, findMin, localization} */

@@ -30,6 +30,9 @@ struct JNIEnv {
     jobject NewDirectByteBuffer(void*, jlong);
     jdoubleArray NewDoubleArray(jsize);
     jlongArray NewLongArray(jsize);
+    jbyteArray NewByteArray(jsize);
+    void SetByteArrayRegion(jbyteArray, jsize, jsize, const jbyte*);
+    void GetByteArrayRegion(jbyteArray, jsize, jsize, jbyte*);
     void SetDoubleArrayRegion(jdoubleArray, jsize, jsize, const jdouble*);
     void SetLongArrayRegion(jlongArray, jsize, jsize, const jlong*);
     void GetLongArrayRegion(jlongArray, jsize, jsize, jlong*);

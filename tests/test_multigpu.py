@@ -33,6 +33,11 @@ def _worker(rank, world, port, q):
     mine = [gv[i] for i in parallel.partition_views(range(4), rank, world)]
     sharded = parallel.fuse_block_view_sharded(ctx, mine, bmin, bsz, p)
     whole = ctx.fuse_block(gv, bmin, bsz, p)
+    # the same exchange behind the C ABI (bs_comm_init + bs_fuse_allreduce on the context's stream)
+    parallel.comm_init_from_torch(ctx)
+    native_sharded = parallel.fuse_block_view_sharded_native(ctx, mine, bmin, bsz, p)
+    assert np.array_equal(native_sharded, sharded)
+    ctx.comm_destroy()
     pairs = [synth.shifted_pair((32, 40, 48), s, seed=40 + i) for i, s in enumerate([(1, 2, 3), (-2, 0, 1), (3, -3, 2)])]
     idx = parallel.shard_items(list(range(3)), rank, world)
     local = [(i, ctx.pcm_pair(*pairs[i]).shift_int) for i in idx]
