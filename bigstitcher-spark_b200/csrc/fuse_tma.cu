@@ -55,6 +55,7 @@ struct __align__(64) ViewDev {
     double inv[12];               // world -> source pixel
     double wlo[3], whi[3];        // world AABB of the view (expanded), second cull test
     const void* data;
+    const float* content;         // content-weight volume (float32, same dims as the volume) or nullptr
     const CUtensorMap* tm_t;      // device copies of the tensor maps (translation box / general box)
     const CUtensorMap* tm_g;
     int dims[3];                  // size of the (full) view: inside test, blending
@@ -318,6 +319,24 @@ __device__ __forceinline__ float wdiv(float swi, float sw) {
     return sw > 0.f ? swi / sw : 0.f;
 }
 
+template <typename T>
+__device__ __forceinline__ float gather8(const T* __restrict__ d, int dx, int dy, int dz, float sx, float sy, float sz) {
+    const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
+    const float rx = sx - fx, ry = sy - fy, rz = sz - fz;
+    const int x0 = min(max((int)fx, 0), dx - 1), y0 = min(max((int)fy, 0), dy - 1), z0 = min(max((int)fz, 0), dz - 1);
+    const int x1 = min(x0 + 1, dx - 1), y1 = min(y0 + 1, dy - 1), z1 = min(z0 + 1, dz - 1);
+    const size_t r00 = ((size_t)z0 * dy + y0) * dx, r01 = ((size_t)z0 * dy + y1) * dx;
+    const size_t r10 = ((size_t)z1 * dy + y0) * dx, r11 = ((size_t)z1 * dy + y1) * dx;
+    const float a000 = (float)__ldg(d + r00 + x0), a001 = (float)__ldg(d + r00 + x1);
+    const float a010 = (float)__ldg(d + r01 + x0), a011 = (float)__ldg(d + r01 + x1);
+    const float a100 = (float)__ldg(d + r10 + x0), a101 = (float)__ldg(d + r10 + x1);
+    const float a110 = (float)__ldg(d + r11 + x0), a111 = (float)__ldg(d + r11 + x1);
+    const float c00 = a000 + rx * (a001 - a000), c01 = a010 + rx * (a011 - a010);
+    const float c10 = a100 + rx * (a101 - a100), c11 = a110 + rx * (a111 - a110);
+    const float c0 = c00 + ry * (c01 - c00), c1 = c10 + ry * (c11 - c10);
+    return c0 + rz * (c1 - c0);
+}
+
 // ------------------------------------------------------------------------------------------ translation tile
 // one z plane of the staged box -> the thread's 2 x 2 x/y-interpolated values (x then y, a + f (b - a)).
 // uint16 -> float without the conversion pipe: PRMT builds 0x4B00hhll = 2^23 + v, differences of two such
@@ -336,6 +355,25 @@ __device__ __forceinline__ void tr_plane(const unsigned int* __restrict__ rowbas
         const float f2 = __uint_as_float(__byte_perm(w1, MAG, sel2));
         r[j][0] = fmaf(fx, f1 - f0, f0 - 8388608.f);
         r[j][1] = fmaf(fx, f2 - f1, f1 - 8388608.f);
+    }
+    c[0] = r[0][0] + fy * (r[1][0] - r[0][0]);
+    c[1] = r[0][1] + fy * (r[1][1] - r[0][1]);
+    c[2] = r[1][0] + fy * (r[2][0] - r[1][0]);
+    c[3] = r[1][1] + fy * (r[2][1] - r[1][1]);
+}
+
+// content-based weights: the same 2 x 2 interpolation of one z plane, taps straight from the float32 content volume in
+// global memory (L1 / L2: lanes cover 65 consecutive floats per row); indices are clamped like the oracle's border
+// extension.  xi: the three clamped x indices, yo: the three clamped row offsets (y * dx), plane: content + z * dy * dx.
+__device__ __forceinline__ void tr_plane_c(const float* __restrict__ plane, const int (&xi)[3], const int (&yo)[3], float fx, float fy,
+                                           float (&c)[4]) {
+    float r[3][2];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const float* row = plane + yo[j];
+        const float t0 = __ldg(row + xi[0]), t1 = __ldg(row + xi[1]), t2 = __ldg(row + xi[2]);
+        r[j][0] = t0 + fx * (t1 - t0);
+        r[j][1] = t1 + fx * (t2 - t1);
     }
     c[0] = r[0][0] + fy * (r[1][0] - r[0][0]);
     c[1] = r[0][1] + fy * (r[1][1] - r[0][1]);
@@ -367,7 +405,7 @@ __device__ __forceinline__ const float* team_weights(const FuseArgs2& a, const V
 }
 
 // PLAT (C == 1 only): the single view's weight is 1 on the whole tile -> the voxel is the sample itself
-template <int C, int OUT, bool PLAT = false>
+template <int C, int OUT, bool PLAT = false, bool CONTENT = false>
 __device__ __forceinline__ void tr_tile(const FuseArgs2& a, const unsigned char* slots, const ViewItem* descs,
                                         const TileRec& T, float* wtab, int& uses, int team, int tid) {
     using OT = typename OutT<OUT>::type;
@@ -376,6 +414,11 @@ __device__ __forceinline__ void tr_tile(const FuseArgs2& a, const unsigned char*
     const float* wz[C];
     unsigned int sel01[C], sel2[C];
     float fx[C], fy[C], fz[C], wxy[C][4], prev[C][4];
+    // content path: per view the volume, its plane pitch, the clamped tap columns / row offsets, first z, previous plane
+    const float* cvol[CONTENT ? C : 1];
+    int cxi[CONTENT ? C : 1][3], cyo[CONTENT ? C : 1][3], cz0[CONTENT ? C : 1], cdz[CONTENT ? C : 1];
+    long long cpl[CONTENT ? C : 1];
+    float cprev[CONTENT ? C : 1][4];
     bool need = false;
 #pragma unroll
     for (int v = 0; v < C; ++v) {
@@ -402,6 +445,19 @@ __device__ __forceinline__ void tr_tile(const FuseArgs2& a, const unsigned char*
         }
         wxy[v][0] = wx0 * wy0; wxy[v][1] = wx1 * wy0; wxy[v][2] = wx0 * wy1; wxy[v][3] = wx1 * wy1;
         tr_plane(base[v], sel01[v], sel2[v], fx[v], fy[v], prev[v]);
+        if (CONTENT) {
+            const ViewDev& V = a.views[d.view];
+            cvol[v] = V.content;
+            cpl[v] = (long long)V.dims[0] * V.dims[1];
+            cz0[v] = d.b0[2];
+            cdz[v] = V.dims[2];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                cxi[v][i] = min(max(d.b0[0] + 2 * lx + i, 0), V.dims[0] - 1);
+                cyo[v][i] = min(max(d.b0[1] + 2 * ly + i, 0), V.dims[1] - 1) * V.dims[0];
+            }
+            tr_plane_c(cvol[v] + (long long)min(max(cz0[v], 0), cdz[v] - 1) * cpl[v], cxi[v], cyo[v], fx[v], fy[v], cprev[v]);
+        }
     }
     const int x = 2 * lx, y = 2 * ly;
     const bool ok0 = y < T.ny && x < T.nx, ok1 = y + 1 < T.ny && x < T.nx;
@@ -413,7 +469,9 @@ __device__ __forceinline__ void tr_tile(const FuseArgs2& a, const unsigned char*
         float swi[4] = {0.f, 0.f, 0.f, 0.f}, sw[4] = {0.f, 0.f, 0.f, 0.f}, res[4];
 #pragma unroll
         for (int v = 0; v < C; ++v) {
-            float cur[4];
+            float cur[4], ccur[4];
+            if (CONTENT)    // issued first: the global loads fly while the shared-memory plane is interpolated
+                tr_plane_c(cvol[v] + (long long)min(max(cz0[v] + k + 1, 0), cdz[v] - 1) * cpl[v], cxi[v], cyo[v], fx[v], fy[v], ccur);
             tr_plane(base[v] + (k + 1) * (BYT * BXT / 2), sel01[v], sel2[v], fx[v], fy[v], cur);
             const float wk = wz[v][k];
 #pragma unroll
@@ -421,7 +479,11 @@ __device__ __forceinline__ void tr_tile(const FuseArgs2& a, const unsigned char*
                 const float val = prev[v][q] + fz[v] * (cur[q] - prev[v][q]);
                 prev[v][q] = cur[q];
                 if (PLAT) { res[q] = val; continue; }
-                const float w = wxy[v][q] * wk;
+                float w = wxy[v][q] * wk;
+                if (CONTENT) {
+                    w *= cprev[v][q] + fz[v] * (ccur[q] - cprev[v][q]);
+                    cprev[v][q] = ccur[q];
+                }
                 if (C == 1) {
                     res[q] = w > 0.f ? val : 0.f;
                 } else {
@@ -441,27 +503,9 @@ __device__ __forceinline__ void tr_tile(const FuseArgs2& a, const unsigned char*
 }
 
 // ------------------------------------------------------------------------------------------ general tile
-template <typename T>
-__device__ __forceinline__ float gather8(const T* __restrict__ d, int dx, int dy, int dz, float sx, float sy, float sz) {
-    const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
-    const float rx = sx - fx, ry = sy - fy, rz = sz - fz;
-    const int x0 = min(max((int)fx, 0), dx - 1), y0 = min(max((int)fy, 0), dy - 1), z0 = min(max((int)fz, 0), dz - 1);
-    const int x1 = min(x0 + 1, dx - 1), y1 = min(y0 + 1, dy - 1), z1 = min(z0 + 1, dz - 1);
-    const size_t r00 = ((size_t)z0 * dy + y0) * dx, r01 = ((size_t)z0 * dy + y1) * dx;
-    const size_t r10 = ((size_t)z1 * dy + y0) * dx, r11 = ((size_t)z1 * dy + y1) * dx;
-    const float a000 = (float)__ldg(d + r00 + x0), a001 = (float)__ldg(d + r00 + x1);
-    const float a010 = (float)__ldg(d + r01 + x0), a011 = (float)__ldg(d + r01 + x1);
-    const float a100 = (float)__ldg(d + r10 + x0), a101 = (float)__ldg(d + r10 + x1);
-    const float a110 = (float)__ldg(d + r11 + x0), a111 = (float)__ldg(d + r11 + x1);
-    const float c00 = a000 + rx * (a001 - a000), c01 = a010 + rx * (a011 - a010);
-    const float c10 = a100 + rx * (a101 - a100), c11 = a110 + rx * (a111 - a110);
-    const float c0 = c00 + ry * (c01 - c00), c1 = c10 + ry * (c11 - c10);
-    return c0 + rz * (c1 - c0);
-}
-
 // > 4 resident views (the 2 x 2 x 2 corners of a tile grid): rolled view loop, both z planes of every
 // output plane recomputed (no per-view register state)
-template <int OUT>
+template <int OUT, bool CONTENT = false>
 __device__ __forceinline__ void tr_tile_many(const FuseArgs2& a, const unsigned char* slots, const ViewItem* descs,
                                              const TileRec& T, float* wtab, int& uses, int team, int tid) {
     using OT = typename OutT<OUT>::type;
@@ -489,13 +533,26 @@ __device__ __forceinline__ void tr_tile_many(const FuseArgs2& a, const unsigned 
             const float* tv = tab + v * WT_N;
             const float wx0 = tv[x], wx1 = tv[x + 1], wy0 = tv[TT_X + y], wy1 = tv[TT_X + y + 1];
             const float wxy[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
-            float c0[4], c1[4];
+            float c0[4], c1[4], w0[4], w1[4];
+            if (CONTENT) {
+                const ViewDev& V = a.views[d.view];
+                int xi[3], yo[3];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    xi[i] = min(max(d.b0[0] + x + i, 0), V.dims[0] - 1);
+                    yo[i] = min(max(d.b0[1] + y + i, 0), V.dims[1] - 1) * V.dims[0];
+                }
+                const long long pl = (long long)V.dims[0] * V.dims[1];
+                tr_plane_c(V.content + (long long)min(max(d.b0[2] + k, 0), V.dims[2] - 1) * pl, xi, yo, fx, fy, w0);
+                tr_plane_c(V.content + (long long)min(max(d.b0[2] + k + 1, 0), V.dims[2] - 1) * pl, xi, yo, fx, fy, w1);
+            }
             tr_plane(base, sel01, sel2, fx, fy, c0);
             tr_plane(base + BYT * BXT / 2, sel01, sel2, fx, fy, c1);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const float val = c0[q] + fz * (c1[q] - c0[q]);
-                const float w = wxy[q] * wk;
+                float w = wxy[q] * wk;
+                if (CONTENT) w *= w0[q] + fz * (w1[q] - w0[q]);
                 swi[q] = swi[q] + w * val;
                 sw[q] = sw[q] + w;
             }
@@ -510,7 +567,7 @@ __device__ __forceinline__ void tr_tile_many(const FuseArgs2& a, const unsigned 
 }
 
 // more views than slots: every tap gathered from global memory (L1/L2)
-template <int OUT>
+template <int OUT, bool CONTENT = false>
 __device__ __forceinline__ void tr_slow_tile(const FuseArgs2& a, const TileRec& T, int tid) {
     using OT = typename OutT<OUT>::type;
     const int lx = tid & 31, ly = tid >> 5;
@@ -529,8 +586,9 @@ __device__ __forceinline__ void tr_slow_tile(const FuseArgs2& a, const TileRec& 
                 const ViewDev& V = a.views[d.view];
                 const float sx = (float)(d.b0[0] + x) + d.o[0], sy = (float)(d.b0[1] + y) + d.o[1];
                 const float sz = (float)(d.b0[2] + k) + d.o[2];
-                const float w = (blend_factor(sx, d.dm1[0], d.border[0], d.inv_range[0], ub) *
-                                 blend_factor(sy, d.dm1[1], d.border[1], d.inv_range[1], ub)) * d.wz[k];
+                float w = (blend_factor(sx, d.dm1[0], d.border[0], d.inv_range[0], ub) *
+                           blend_factor(sy, d.dm1[1], d.border[1], d.inv_range[1], ub)) * d.wz[k];
+                if (CONTENT && w > 0.f) w *= gather8(V.content, V.dims[0], V.dims[1], V.dims[2], sx, sy, sz);
                 if (!(w > 0.f)) continue;
                 const float val = gather8((const unsigned short*)V.data, V.wdims[0], V.wdims[1], V.wdims[2],
                                           sx - (float)V.woff[0], sy - (float)V.woff[1], sz - (float)V.woff[2]);
@@ -649,7 +707,7 @@ extern __shared__ __align__(1024) unsigned char fuse2_smem[];
 // Persistent: one CTA per SM; the producer warp draws work records (z-runs of one tile column) from a global
 // counter and streams their tiles through the slot / tile-record rings without ever draining the pipeline;
 // the two consumer teams take alternate tile records until each receives a terminator record.
-template <bool GENERAL, int OUT>
+template <bool GENERAL, int OUT, bool CONTENT = false>
 __global__ void __launch_bounds__(NTHREADS, 1) fuse_tma_kernel(const __grid_constant__ FuseArgs2 a) {
     constexpr int NST = GENERAL ? NST_G : NST_T;
     constexpr int SLOT = GENERAL ? SLOT_G : SLOT_T;
@@ -771,20 +829,29 @@ __global__ void __launch_bounds__(NTHREADS, 1) fuse_tma_kernel(const __grid_cons
         } else if (GENERAL) {
             gen_tile<OUT>(a, slots, descs, T, ttid);
         } else if (T.mode == 1) {
-            switch (T.count) {
-                case 1:
-                    if ((descs[T.it0 % NST].flags & (VI_PLAT_X | VI_PLAT_Y | VI_PLAT_Z)) == (VI_PLAT_X | VI_PLAT_Y | VI_PLAT_Z))
-                        tr_tile<1, OUT, true>(a, slots, descs, T, wt, uses, team, ttid);
-                    else
-                        tr_tile<1, OUT>(a, slots, descs, T, wt, uses, team, ttid);
-                    break;
-                case 2: tr_tile<2, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
-                case 3: tr_tile<3, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
-                case 4: tr_tile<4, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
-                default: tr_tile_many<OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
+            if (CONTENT) {
+                // content weights ride along from global memory; register state for <= 2 views, rolled beyond
+                switch (T.count) {
+                    case 1: tr_tile<1, OUT, false, true>(a, slots, descs, T, wt, uses, team, ttid); break;
+                    case 2: tr_tile<2, OUT, false, true>(a, slots, descs, T, wt, uses, team, ttid); break;
+                    default: tr_tile_many<OUT, true>(a, slots, descs, T, wt, uses, team, ttid); break;
+                }
+            } else {
+                switch (T.count) {
+                    case 1:
+                        if ((descs[T.it0 % NST].flags & (VI_PLAT_X | VI_PLAT_Y | VI_PLAT_Z)) == (VI_PLAT_X | VI_PLAT_Y | VI_PLAT_Z))
+                            tr_tile<1, OUT, true>(a, slots, descs, T, wt, uses, team, ttid);
+                        else
+                            tr_tile<1, OUT>(a, slots, descs, T, wt, uses, team, ttid);
+                        break;
+                    case 2: tr_tile<2, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
+                    case 3: tr_tile<3, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
+                    case 4: tr_tile<4, OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
+                    default: tr_tile_many<OUT>(a, slots, descs, T, wt, uses, team, ttid); break;
+                }
             }
         } else {
-            tr_slow_tile<OUT>(a, T, ttid);
+            tr_slow_tile<OUT, CONTENT>(a, T, ttid);
         }
         __syncwarp();
         if (lane == 0) {
@@ -871,11 +938,11 @@ Fuse2Ws* ws_of(bs_ctx* ctx) {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-template <bool GENERAL>
+template <bool GENERAL, bool CONTENT = false>
 void launch_kernel(int out_dtype, int grid, size_t smem, cudaStream_t s, const FuseArgs2& a) {
-    if (out_dtype == BS_DTYPE_F32) fuse_tma_kernel<GENERAL, BS_DTYPE_F32><<<grid, NTHREADS, smem, s>>>(a);
-    else if (out_dtype == BS_DTYPE_U16) fuse_tma_kernel<GENERAL, BS_DTYPE_U16><<<grid, NTHREADS, smem, s>>>(a);
-    else fuse_tma_kernel<GENERAL, BS_DTYPE_U8><<<grid, NTHREADS, smem, s>>>(a);
+    if (out_dtype == BS_DTYPE_F32) fuse_tma_kernel<GENERAL, BS_DTYPE_F32, CONTENT><<<grid, NTHREADS, smem, s>>>(a);
+    else if (out_dtype == BS_DTYPE_U16) fuse_tma_kernel<GENERAL, BS_DTYPE_U16, CONTENT><<<grid, NTHREADS, smem, s>>>(a);
+    else fuse_tma_kernel<GENERAL, BS_DTYPE_U8, CONTENT><<<grid, NTHREADS, smem, s>>>(a);
 }
 
 constexpr size_t smem_bytes(bool general) {
@@ -887,12 +954,25 @@ constexpr size_t smem_bytes(bool general) {
 bool eligible(bs_ctx* ctx, const bs_view* views, int n_views, const bs_fuse_params* p) {
     const char* e = getenv("BS_FUSE_LEGACY");
     if (e && *e && *e != '0') return false;
-    if (!(p->fusion_type == BS_FUSE_AVG || p->fusion_type == BS_FUSE_AVG_BLEND)) return false;
+    const bool content = p->fusion_type == BS_FUSE_AVG_CONTENT || p->fusion_type == BS_FUSE_AVG_BLEND_CONTENT;
+    if (!(p->fusion_type == BS_FUSE_AVG || p->fusion_type == BS_FUSE_AVG_BLEND || content)) return false;
     if (p->interpolation != 1 || p->blend_lut_n != 0) return false;
     for (int i = 0; i < n_views; ++i) {
         auto it = ctx->vols.find(views[i].vol_handle);
         if (it == ctx->vols.end()) return false;   // the legacy path reports the error
         if (!ensure_tmaps(ctx, it->second)) return false;
+        if (content) {
+            // content weights ride along in the translation kernel only: whole (non-windowed) views, identity linear part
+            auto ic = ctx->vols.find(views[i].content_handle);
+            if (ic == ctx->vols.end() || ic->second.dtype != BS_DTYPE_F32 || ic->second.dims[0] != it->second.dims[0] ||
+                ic->second.dims[1] != it->second.dims[1] || ic->second.dims[2] != it->second.dims[2] || views[i].full_dims[0] > 0)
+                return false;
+            double inv[12];
+            if (!bs_invert34(views[i].src_to_world, inv)) return false;
+            if (!(inv[0] == 1.0 && inv[1] == 0.0 && inv[2] == 0.0 && inv[4] == 0.0 && inv[5] == 1.0 && inv[6] == 0.0 &&
+                  inv[8] == 0.0 && inv[9] == 0.0 && inv[10] == 1.0))
+                return false;
+        }
         for (int k = 0; k < 3; ++k)
             if (!(views[i].blend_range[k] > 0.f) && p->fusion_type == BS_FUSE_AVG_BLEND) return false;
     }
@@ -918,6 +998,12 @@ int fuse2_launch(bs_ctx* ctx, const bs_view* views, int n_views, int nb, const l
               m[9] == 0.0 && m[10] == 1.0))
             general = true;
         d.data = vol.dev;
+        d.content = nullptr;
+        if (p->fusion_type == BS_FUSE_AVG_CONTENT || p->fusion_type == BS_FUSE_AVG_BLEND_CONTENT) {
+            bs_volume& cv = ctx->vols.find(views[i].content_handle)->second;
+            { int rc = bs_volume_acquire(ctx, cv); if (rc) return rc; }
+            d.content = (const float*)cv.dev;
+        }
         d.tm_t = (const CUtensorMap*)vol.tmaps_dev;
         d.tm_g = (const CUtensorMap*)vol.tmaps_dev + 1;
         const bool windowed = views[i].full_dims[0] > 0;
@@ -1047,7 +1133,8 @@ int fuse2_launch(bs_ctx* ctx, const bs_view* views, int n_views, int nb, const l
     const unsigned char* md = (const unsigned char*)W->meta_dev;
     const ViewDev* dviews = (const ViewDev*)(md + off_views);
     const BlockDev* dblocks = (const BlockDev*)(md + off_blocks);
-    const int use_blend = p->fusion_type == BS_FUSE_AVG_BLEND ? 1 : 0;
+    const int use_blend = (p->fusion_type == BS_FUSE_AVG_BLEND || p->fusion_type == BS_FUSE_AVG_BLEND_CONTENT) ? 1 : 0;
+    const bool content = p->fusion_type == BS_FUSE_AVG_CONTENT || p->fusion_type == BS_FUSE_AVG_BLEND_CONTENT;
     int max_tiles = 0;
     for (int b = 0; b < nb; ++b) max_tiles = std::max(max_tiles, hb[b].ntiles);
     {
@@ -1063,6 +1150,9 @@ int fuse2_launch(bs_ctx* ctx, const bs_view* views, int n_views, int nb, const l
         BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<false, BS_DTYPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, st));
         BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<false, BS_DTYPE_U16>, cudaFuncAttributeMaxDynamicSharedMemorySize, st));
         BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<false, BS_DTYPE_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, st));
+        BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<false, BS_DTYPE_F32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st));
+        BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<false, BS_DTYPE_U16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st));
+        BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<false, BS_DTYPE_U8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st));
         BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<true, BS_DTYPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg));
         BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<true, BS_DTYPE_U16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg));
         BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<true, BS_DTYPE_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg));
@@ -1085,6 +1175,7 @@ int fuse2_launch(bs_ctx* ctx, const bs_view* views, int n_views, int nb, const l
         bs_launch_scope scope(ctx, "fuse");
         const int grid = (int)std::min<size_t>(work.size(), (size_t)ctx->sm_count);
         if (general) launch_kernel<true>(p->out_dtype, grid, smem_bytes(true), ctx->stream, a);
+        else if (content) launch_kernel<false, true>(p->out_dtype, grid, smem_bytes(false), ctx->stream, a);
         else launch_kernel<false>(p->out_dtype, grid, smem_bytes(false), ctx->stream, a);
     }
     BS_CUDA(ctx, cudaGetLastError());
