@@ -613,7 +613,7 @@ def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
             variants["content_based"] = {"value": nvox_total / (ms_c / 1000.0) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_c,
                                          "fusion_type": "AVG_BLEND_CONTENT", "sigma": [20.0, 40.0],
                                          "alg_bytes_per_voxel": 12.54, "kernel": "fuse_tma_kernel<translation, content> (content taps from global memory)",
-                                         "frac_of_hbm_peak": round(12.54 * nvox_total / (ms_c / 1000.0) / 1e9 / peak_gbs, 4),
+                                         "frac_of_hbm_peak": round(12.54 * nvox_rank / (ms_c / 1000.0) / 1e9 / peak_gbs, 4),
                                          "content_precompute_s": round(pre_s, 3),
                                          "content_volumes": len(chandle)}
             for h in chandle.values():
