@@ -97,3 +97,22 @@ def test_non_equal_transformations_branch_virtual_fusion(ctx):
     o = po.pcm_shift(ra, rb)
     assert tuple(np.rint(T[:, 3]).astype(int)) == o.shift_int
     assert np.allclose(T[:, 3], o.shift_sub, atol=2e-3) and abs(r - o.r) < 1e-5
+
+
+def test_config5_shape_end_to_end_runner(tmp_path):
+    """BASELINE configs[4] shape at toy size through the real command bodies on the GPU: synthetic lightsheet grid on
+    disk (XML + BDV-N5), `stitching` (tiles uploaded once, crops cut on the device), `create-fusion-container`,
+    `affine-fusion` with block-wise windowed source staging; the planted jitter must come back for every pair."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "run_config5.py"), "--grid", "3x2x2", "--tile", "96x80x64",
+                        "--overlap", "0.25", "--workdir", str(tmp_path / "cfg5")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["tiles"] == 12 and d["stitching"]["pairs"] >= 12
+    ok, total = (int(v) for v in d["stitching"]["planted_jitter_recovered"].split("/"))
+    assert total >= 12 and ok == total
+    assert d["fusion"]["mvoxels_per_s"] > 0 and d["launches"] > 0

@@ -135,3 +135,34 @@ def test_bench_reference_arm_json_contract():
     assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and "sample" in d["cpu_baseline"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] and "workload" in d["config"]
+
+
+def test_stitch_pairs_resident_batches_respect_the_budget():
+    """The resident-tile work queue: with a budget of two tiles every pair still gets its result (tiles are re-uploaded
+    across batches), identical to the unconstrained run."""
+    from bsgpu import stitching as bst
+    from tests import synth
+    from tests.fake_ctx import FakeContext
+    G = synth.field((40, 40, 150), seed=4, sigma=1.0)
+    tiles, models = {}, {}
+    for i in range(4):
+        tiles[(0, i)] = synth.tile_from(G, (4, 4, 4 + 30 * i + (i % 2)), (32, 32, 48), 80 + i, noise=3)
+        models[(0, i)] = synth.translation((30 * i, 0, 0))
+    pairs = [((0, 0), (0, 1)), ((0, 1), (0, 2)), ((0, 2), (0, 3))]
+
+    class Counting(FakeContext):
+        uploads = 0
+
+        def volume_upload(self, vol):
+            Counting.uploads += 1
+            return super().volume_upload(vol)
+
+    ctx = Counting()
+    full = bst.stitch_pairs(pairs, tiles, models, None, (1, 1, 1), ctx)
+    assert Counting.uploads == 4 and not ctx.vols
+    Counting.uploads = 0
+    small = bst.stitch_pairs(pairs, tiles, models, None, (1, 1, 1), ctx, max_resident_bytes=2 * tiles[(0, 0)].nbytes)
+    assert Counting.uploads == 6 and not ctx.vols          # three batches of two tiles
+    for a, b in zip(full, small):
+        assert a is not None and np.array_equal(a.transform, b.transform) and a.r == b.r
+    assert [tuple(np.rint(r.transform[:, 3]).astype(int)) for r in full] == [(1, 0, 0), (-1, 0, 0), (1, 0, 0)]
