@@ -596,8 +596,23 @@ def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
         vd_rot = {v: dict(src_to_world=models_rot[v], vol_handle=handles[v], blend_border=bf.adjust_blending(models_rot[v])[0],
                           blend_range=bf.adjust_blending(models_rot[v])[1]) for v in mine}
         ms_r, _, _ = run_variant("AVG_BLEND", vd_rot, max(1, min(args.steps, 2)))
-        variants["rotated_0.5deg"] = {"value": nvox_total / (ms_r / 1000.0) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_r,
-                                      "kernel": "fuse_tma_kernel<general>"}
+        variants["rotated_0.5deg_z"] = {"value": nvox_total / (ms_r / 1000.0) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_r,
+                                        "kernel": "fuse_tma_kernel<general> (xy-affine z-marching tiles for <= 2 views, per-voxel tiles otherwise)"}
+        # a rotation about an oblique axis has no exploitable structure: every voxel samples 8 taps
+        ax = np.array([1.0, 1.0, 1.0]) / np.sqrt(3.0)
+        th = np.deg2rad(0.5)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        Rg = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+        models_obl = []
+        for v in range(nviews):
+            t = np.asarray(models[v])[:, 3]
+            c = np.array([tile / 2, tile / 2, tile / 2])
+            models_obl.append(np.hstack([Rg, (t + c - Rg @ c)[:, None]]))
+        vd_obl = {v: dict(src_to_world=models_obl[v], vol_handle=handles[v], blend_border=bf.adjust_blending(models_obl[v])[0],
+                          blend_range=bf.adjust_blending(models_obl[v])[1]) for v in mine}
+        ms_o, _, _ = run_variant("AVG_BLEND", vd_obl, 1)
+        variants["rotated_0.5deg_oblique"] = {"value": nvox_total / (ms_o / 1000.0) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms_o,
+                                              "kernel": "fuse_tma_kernel<general> (per-voxel 8-tap tiles)"}
         if not args.skip_fusion_content:
             # content-based weights G_s2 * (I - G_s1 * I)^2 (sigma 20 / 40) are precomputed per DISTINCT tile volume
             t0 = time.perf_counter()

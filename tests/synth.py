@@ -61,3 +61,12 @@ def subpixel_pair(shape_zyx, shift_xyz, seed=0, margin=24, sigma=1.5, noise=20.0
     a = tile_from(G, (margin,) * 3, shape_zyx, 1000 + seed, noise, dtype)
     b = tile_from(G2, (margin,) * 3, shape_zyx, 2000 + seed, noise, dtype)
     return a, b
+
+
+def rot_x(deg, center_xyz=(0, 0, 0)):
+    """3x4 rotation about x through ``center`` (couples y and z: no xy-affine structure)."""
+    a = np.deg2rad(deg)
+    R = np.array([[1, 0, 0], [0, np.cos(a), -np.sin(a)], [0, np.sin(a), np.cos(a)]], dtype=np.float64)
+    c = np.asarray(center_xyz, dtype=np.float64)
+    t = c - R @ c
+    return np.hstack([R, t[:, None]])
