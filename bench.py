@@ -511,7 +511,8 @@ def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
             chunk = grid[c0:c0 + CH]
             lo = tuple(min(b[0][d] for b in chunk) for d in range(3))
             hi = tuple(max(b[0][d] + b[1][d] - 1 for b in chunk) for d in range(3))
-            vids = bf.find_overlapping_views(vdims, regs, lo, hi, mine)
+            vregs = {v: view_dicts[v]["src_to_world"] for v in mine}      # the variant's own registrations
+            vids = bf.find_overlapping_views(vdims, vregs, lo, hi, mine)
             views = ctx.make_views(view_dicts[v] for v in vids)
             ptrs = []
             for (_, sz, _g) in chunk:
