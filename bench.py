@@ -437,6 +437,15 @@ def run_gpu(args, rank, world, local_rank):
     if fusion_obj is not None and cpu_fusion is not None:
         fusion_obj["cpu_baseline"] = cpu_fusion
 
+    # ---------------------------------------------------------------- DoG interest points (BASELINE configs[3], stretch row)
+    dog_obj = None
+    if not args.skip_dog:
+        try:
+            torch.cuda.empty_cache()
+            dog_obj = bench_dog(args, ctx, stream, dev, rank, world, timed, peak_gbs)
+        except Exception as exc:
+            dog_obj = {"value": None, "error": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
         bpp = pcm_bytes_per_pair(n ** 3, P, pearson_px_mean)
         dom = max(kern, key=lambda k: kern[k]["ms"]) if kern else None
@@ -468,12 +477,60 @@ def run_gpu(args, rank, world, local_rank):
                        "mean_pearson_candidates": ncand_mean},
             "e2e": e2e,
             "gpu_launches": int(launches), "wall_ms_timed": wall_ms, "clocks": clocks,
-            "roofline": roof, "cpu_baseline": cpu, "fusion": fusion_obj,
+            "roofline": roof, "cpu_baseline": cpu, "fusion": fusion_obj, "dog": dog_obj,
         }
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_dog(args, ctx, stream, dev, rank, world, timed, peak_gbs):
+    """SparkInterestPointDetection's DoG (sigma 1.8, threshold 0.008, quadratic localisation) on one synthetic bead tile
+    per rank, processed in the reference's 512x512x128 blocks (+1 px halo inside the image, J/SparkInterestPointDetection.java:
+    397-424).  Mvoxels/s of tile voxels; algorithmic bytes per voxel = 2 (uint16 read) -- everything else is scratch."""
+    import torch
+    import bsgpu
+    from bsgpu import fusion as bf
+    n = args.dog_size
+    g = torch.Generator(device=dev)
+    g.manual_seed(77 + rank)
+    vol = torch.rand((n // 4 if n >= 512 else n, n, n), generator=g, device=dev) * 60 + 180     # [z, y, x] background
+    nz = vol.shape[0]
+    nb = 400
+    cz = torch.randint(4, nz - 4, (nb,), generator=g, device=dev)
+    cy = torch.randint(4, n - 4, (nb,), generator=g, device=dev)
+    cx = torch.randint(4, n - 4, (nb,), generator=g, device=dev)
+    r = torch.arange(-4, 5, device=dev, dtype=torch.float32)
+    bead = 3000.0 * torch.exp(-(r[:, None, None] ** 2 + r[None, :, None] ** 2 + r[None, None, :] ** 2) / (2 * 1.8 ** 2))
+    for i in range(nb):
+        z, y, x = int(cz[i]), int(cy[i]), int(cx[i])
+        vol[z - 4:z + 5, y - 4:y + 5, x - 4:x + 5] += bead
+    tile = torch.clamp(torch.round(vol), 0, 32767).to(torch.int16).contiguous()
+    del vol
+    torch.cuda.synchronize()
+    h = ctx.volume_wrap(tile, (n, n, nz), bsgpu.native.DTYPE_U16)
+    blocks = []
+    for (off, size, _) in bf.grid_create((n, n, nz), (512, 512, 128)):
+        lo = [max(0, off[d] - 1) for d in range(3)]
+        hi = [min((n, n, nz)[d] - 1, off[d] + size[d]) for d in range(3)]
+        blocks.append((lo, [hi[d] - lo[d] + 1 for d in range(3)]))
+    found = []
+
+    def step():
+        found.clear()
+        for lo, sz in blocks:
+            found.extend(ctx.dog_detect(h, lo, sz, sigma=1.8, threshold=0.008, min_intensity=0.0, max_intensity=4000.0))
+    step()
+    nfound = len({p[2] for p in found})
+    ms, _ = timed(step, max(1, min(args.steps, 2)))
+    ms /= max(1, min(args.steps, 2))
+    nvox = n * n * nz
+    ctx.volume_free(h)
+    return {"metric": "DoG interest points, Mvoxels/sec", "value": world * nvox / (ms / 1000.0) / 1e6, "unit": "Mvoxels/s", "ms_per_step": ms,
+            "config": {"workload": f"one {n}x{n}x{nz} uint16 bead tile per GPU, {len(blocks)} blocks of 512x512x128 (+1 px), sigma 1.8, "
+                                   f"threshold 0.008, MAX, quadratic localisation", "planted_beads": nb, "detections": nfound},
+            "frac_of_hbm_peak": round(2.0 * nvox / (ms / 1000.0) / 1e9 / peak_gbs, 4)}
 
 
 def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src):
@@ -749,6 +806,8 @@ def main():
     ap.add_argument("--skip-oracle", action="store_true", help="skip the oracle spot checks outside the timed region")
     ap.add_argument("--skip-fusion-variants", action="store_true")
     ap.add_argument("--skip-fusion-content", action="store_true")
+    ap.add_argument("--skip-dog", action="store_true")
+    ap.add_argument("--dog-size", type=int, default=1024)
     ap.add_argument("--fusion-blocks-per-call", type=int, default=64)
     ap.add_argument("--skip-pcm", action="store_true", help="debug: tiny PCM workload")
     ap.add_argument("--ref-full", action="store_true", help="reference arm: run all warm-up steps too")

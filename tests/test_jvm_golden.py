@@ -73,3 +73,33 @@ def test_fusion_oracle_matches_upstream():
             got = fo.fuse_block(views, c["block_min"], c["block_size"], types[name])
             err = np.abs(got - want) / np.maximum(np.abs(want), 250.0)
             assert (err > 1e-4).mean() < 1e-3, (c["name"], name, float(err.max()))
+
+
+@needs_jvm
+@pytest.mark.gpu
+def test_cuda_path_matches_upstream(ctx):
+    """the product itself (through the C ABI) against the JVM vectors: the end of the parity chain"""
+    for c in _manifest()["pcm"]:
+        dims = c["dims"]
+        a = np.fromfile(os.path.join(IN, c["a"]), "<u2").reshape(dims[::-1])
+        b = np.fromfile(os.path.join(IN, c["b"]), "<u2").reshape(dims[::-1])
+        j = json.load(open(os.path.join(JVM, f"pcm_{c['name']}.json")))
+        g = ctx.pcm_pair(a, b, ctx.pcm_params(c["peaksToCheck"], c["doSubpixel"], c["minOverlap"]))
+        assert bool(g.found) == bool(j["found"])
+        if j["found"]:
+            assert np.allclose(g.shift_sub, j["shift"], atol=1e-3) and abs(g.r - j["r"]) < 1e-6
+    for c in _manifest()["fusion"]:
+        handles, gv = [], []
+        for v in c["views"]:
+            img = np.fromfile(os.path.join(IN, v["file"]), "<u2").reshape(v["dims"][::-1])
+            M = np.array(v["model"]).reshape(3, 4)
+            border, rng = fo.adjust_blending(M)
+            handles.append(ctx.volume_upload(img))
+            gv.append(dict(src_to_world=M, vol_handle=handles[-1], blend_border=border, blend_range=rng))
+        for name in c["fusion_types"]:
+            want = np.fromfile(os.path.join(JVM, f"fusion_{c['name']}_{name}.raw"), "<f4").reshape(c["block_size"][::-1])
+            got = ctx.fuse_block(gv, c["block_min"], c["block_size"], ctx.fuse_params(name))
+            err = np.abs(got - want) / np.maximum(np.abs(want), 250.0)
+            assert (err > 1e-4).mean() < 1e-3, (c["name"], name, float(err.max()))
+        for h in handles:
+            ctx.volume_free(h)
