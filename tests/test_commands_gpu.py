@@ -114,5 +114,5 @@ def test_config5_shape_end_to_end_runner(tmp_path):
     d = json.loads(r.stdout.strip().splitlines()[-1])
     assert d["tiles"] == 12 and d["stitching"]["pairs"] >= 12
     ok, total = (int(v) for v in d["stitching"]["planted_jitter_recovered"].split("/"))
-    assert total >= 12 and ok == total
+    assert total >= 16 and ok == total          # every confidently correlated pair (r >= 0.6) returns its planted jitter
     assert d["fusion"]["mvoxels_per_s"] > 0 and d["launches"] > 0

@@ -94,15 +94,20 @@ def main():
     barrier()
     t_st = time.perf_counter() - t0
     npairs = len(raw)
-    ok = 0
+    ok = ok_total = 0
+    wrong = []
     if rank == 0:
         by_setup = {tl["setup"]: tl for tl in tiles}
         for r in raw:
-            if r is None:
+            if r is None or r.r < 0.6:       # the `stitching` command itself filters at --minR (default 0.3)
                 continue
             (a, b) = r.pair
             want = np.subtract(by_setup[b[1]]["jitter"], by_setup[a[1]]["jitter"])
-            ok += int(np.all(np.abs(np.asarray(r.transform)[:, 3] - want) < 0.75))
+            good = bool(np.all(np.abs(np.asarray(r.transform)[:, 3] - want) < 0.75))
+            ok += int(good)
+            ok_total += 1
+            if not good:
+                wrong.append((a[1], b[1], round(float(r.r), 3)))
     # ---- fusion
     out = os.path.join(args.workdir, "fused.n5")
     if rank == 0:
@@ -119,7 +124,7 @@ def main():
         print(json.dumps({"config": f"BASELINE configs[4] shape: {args.grid} grid of {args.tile} uint16 tiles, {int(args.overlap * 100)} % overlap, "
                                     f"jitter <= 5 px, N5 raw on {args.workdir}", "n_gpus": world, "tiles": len(tiles),
                           "stitching": {"pairs": npairs, "seconds": round(t_st, 3), "pairs_per_s": round(npairs / t_st, 2), "ds": list(ds),
-                                        "planted_jitter_recovered": f"{ok}/{sum(r is not None for r in raw)}"},
+                                        "planted_jitter_recovered": f"{ok}/{ok_total}", "of_pairs_with_r_above": 0.6, "wrong": wrong[:8]},
                           "fusion": {"dims": dims, "seconds": round(t_fu, 3), "mvoxels_per_s": round(nvox / t_fu / 1e6, 1), "dtype": "uint16"},
                           "dataset_write_s": round(t_data, 2), "launches": ctx.launch_count()}), flush=True)
     ctx.close()
