@@ -139,6 +139,14 @@ class _Sink:
         else:
             self.store.save_block(dataset, block, grid_pos)
 
+    def save_chunk(self, dataset, block, chunk_pos):
+        """One storage block / chunk exactly as the device packed it (N5: already big-endian)."""
+        if self.is_zarr:
+            gx, gy, gz = chunk_pos
+            self.store.write_chunk(dataset, (self.t, self.c, gz, gy, gx), block)
+        else:
+            self.store.write_block(dataset, chunk_pos, block)
+
     def read_region(self, dataset, mn, size):
         if self.is_zarr:
             return self.store.read_region(dataset, mn, size, self.c, self.t)
@@ -251,6 +259,10 @@ def _fuse_volume_blockwise(ctx, data, src, sink, meta, levels, view_ids, fusion_
     params = ctx.fuse_params(ft, interpolation, od, 0, float(meta["min_intensity"] or 0.0), float(meta["max_intensity"] or 65535.0))
     np_dt = native._BS2NP[od]
     s0 = levels[0]["dataset"]
+    # blocks that go straight to the container leave the device as STORAGE chunks in the container's byte order
+    # (N5 payloads are big-endian): the host neither re-strides nor swaps them
+    chunk_params = ctx.fuse_params(ft, interpolation, od, 0, float(meta["min_intensity"] or 0.0),
+                                   float(meta["max_intensity"] or 65535.0), out_big_endian=not sink.is_zarr)
 
     # ---- per view: mipmap level by the reference's rule, level volume size, source -> world of that level
     info = {}
@@ -324,13 +336,14 @@ def _fuse_volume_blockwise(ctx, data, src, sink, meta, levels, view_ids, fusion_
                     else:
                         for c0 in range(0, len(todo), blocks_per_call):
                             chunk = todo[c0:c0 + blocks_per_call]
+                            cells = [cell for gb in chunk for cell in _storage_cells(gb, bs)]
                             try:
-                                outs = _fuse_chunk(ctx, chunk, bb_min, vdims, vregs, views, params, np_dt)
+                                outs = _fuse_chunk(ctx, cells, bb_min, vdims, vregs, views, chunk_params, np_dt)
                             except native.BsError:
                                 failed.extend(chunk)
                                 continue
-                            for (off, size, gpos), blk in zip(chunk, outs):
-                                sink.save(s0, blk, gpos)
+                            for (off, size, gpos), blk in zip(cells, outs):
+                                sink.save_chunk(s0, blk, gpos)
                     todo = failed
             finally:
                 for h in staged.values():
@@ -393,6 +406,20 @@ def _fuse_block_with_pyramid(ctx, gb, bb_min, vdims, vregs, views, params, np_dt
                               [int(v) for v in lv["dimensions"][:3]], bs)
     finally:
         ctx.volume_free(cur_h)
+
+
+def _storage_cells(gb, bs):
+    """The storage blocks of one super-block: [(offset, size, grid position)] in the container's block grid."""
+    off, size, gpos = gb
+    cells = []
+    for kz in range(-(-size[2] // bs[2])):
+        for ky in range(-(-size[1] // bs[1])):
+            for kx in range(-(-size[0] // bs[0])):
+                k = (kx, ky, kz)
+                cells.append((tuple(int(off[d] + k[d] * bs[d]) for d in range(3)),
+                              tuple(int(min(bs[d], size[d] - k[d] * bs[d])) for d in range(3)),
+                              tuple(int(gpos[d] + k[d]) for d in range(3))))
+    return cells
 
 
 def _fuse_chunk(ctx, chunk, bb_min, vdims, vregs, views, params, np_dt):

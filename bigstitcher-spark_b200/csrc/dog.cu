@@ -82,15 +82,20 @@ __global__ void __launch_bounds__(256) k_dog_blur(const __grid_constant__ BlurAr
         const int y = (int)(r % a.dims[1]), z = (int)(r / a.dims[1]);
         const int p = a.axis == 0 ? x : (a.axis == 1 ? y : z);
         const long long base = i - (long long)p * stride;
+        // symmetric pairing, outermost taps first: (in[p - t] + in[p + t]) * k[t].  Across a mirrored image border
+        // the two sides see the same pairs, so mirrored outputs are bit-identical and a border extremum ties with
+        // its mirror image exactly (ties are kept) -- the symmetric-kernel evaluation of imglib2 / scipy.
         float sa = 0.f, sb = 0.f;
-        for (int t = -a.ra; t <= a.ra; ++t) {
-            const int q = min(max(p + t, 0), len - 1);
-            sa = fmaf(a.ka[t + a.ra], __ldg(a.in_a + base + (long long)q * stride), sa);
+        for (int t = a.ra; t >= 1; --t) {
+            const int q0 = max(p - t, 0), q1 = min(p + t, len - 1);
+            sa = fmaf(a.ka[a.ra - t], __ldg(a.in_a + base + (long long)q0 * stride) + __ldg(a.in_a + base + (long long)q1 * stride), sa);
         }
-        for (int t = -a.rb; t <= a.rb; ++t) {
-            const int q = min(max(p + t, 0), len - 1);
-            sb = fmaf(a.kb[t + a.rb], __ldg(a.in_b + base + (long long)q * stride), sb);
+        sa = fmaf(a.ka[a.ra], __ldg(a.in_a + i), sa);
+        for (int t = a.rb; t >= 1; --t) {
+            const int q0 = max(p - t, 0), q1 = min(p + t, len - 1);
+            sb = fmaf(a.kb[a.rb - t], __ldg(a.in_b + base + (long long)q0 * stride) + __ldg(a.in_b + base + (long long)q1 * stride), sb);
         }
+        sb = fmaf(a.kb[a.rb], __ldg(a.in_b + i), sb);
         if (a.out_b) { a.out_a[i] = sa; a.out_b[i] = sb; }
         else a.out_a[i] = (sa - sb) * a.scale;
     }

@@ -708,6 +708,8 @@ void bs_fuse_default_params(bs_fuse_params* p) {
     p->blend_lut_n = 0;
     p->min_intensity = 0.0;
     p->max_intensity = 65535.0;
+    p->out_big_endian = 0;
+    p->reserved = 0;
 }
 
 }  // extern "C"
@@ -748,6 +750,8 @@ int bs_fuse_finish(bs_ctx* ctx, const float* sum_wi_dev, const float* sum_w_dev,
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!sum_wi_dev || !sum_w_dev || !out || !params || n <= 0)
         return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse_finish: bad argument");
+    if (params->out_big_endian)
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse_finish: out_big_endian is only supported by bs_fuse_block(s)");
     BS_CUDA(ctx, cudaSetDevice(ctx->device));
     FuseArgs a;
     memset(&a, 0, sizeof(a));

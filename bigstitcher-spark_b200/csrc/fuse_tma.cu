@@ -115,6 +115,7 @@ struct FuseArgs2 {
     int nwork;
     int use_blend;
     int xyaff;                    // general kernel: every view is an xy-affine + z-translation (fast z-marching tiles)
+    int swap;                     // bs_fuse_params.out_big_endian: 2-/4-byte elements are stored byte-swapped
     double cmin, cscale, ctop;
 };
 
@@ -280,21 +281,24 @@ __global__ void fuse_plan2_kernel(const ViewDev* __restrict__ views, const Block
 }
 
 // ------------------------------------------------------------------------------------------ output
-template <int OUT>
-__device__ __forceinline__ void store1(const FuseArgs2& a, void* p, float res) {
-    if (OUT == BS_DTYPE_F32) {
-        __stcs((float*)p, res);
-    } else {
-        double c = floor(((double)res - a.cmin) * a.cscale + 0.5);
-        c = fmin(fmax(c, 0.0), a.ctop);
-        if (OUT == BS_DTYPE_U16) *(unsigned short*)p = (unsigned short)c;
-        else *(unsigned char*)p = (unsigned char)c;
-    }
-}
+__device__ __forceinline__ unsigned int bswap32(unsigned int v) { return __byte_perm(v, 0u, 0x0123); }
+__device__ __forceinline__ unsigned int bswap16x2(unsigned int v) { return __byte_perm(v, 0u, 0x2301); }
+
 template <int OUT>
 __device__ __forceinline__ unsigned int conv_int(const FuseArgs2& a, float res) {
     double c = floor(((double)res - a.cmin) * a.cscale + 0.5);
     return (unsigned int)fmin(fmax(c, 0.0), a.ctop);
+}
+template <int OUT>
+__device__ __forceinline__ void store1(const FuseArgs2& a, void* p, float res) {
+    if (OUT == BS_DTYPE_F32) {
+        if (a.swap) __stcs((unsigned int*)p, bswap32(__float_as_uint(res)));
+        else __stcs((float*)p, res);
+    } else {
+        const unsigned int c = conv_int<OUT>(a, res);
+        if (OUT == BS_DTYPE_U16) *(unsigned short*)p = (unsigned short)(a.swap ? bswap16x2(c) : c);
+        else *(unsigned char*)p = (unsigned char)c;
+    }
 }
 template <int OUT> struct OutT { using type = float; };
 template <> struct OutT<BS_DTYPE_U16> { using type = unsigned short; };
@@ -305,12 +309,21 @@ template <int OUT>
 __device__ __forceinline__ void store_pair(const FuseArgs2& a, typename OutT<OUT>::type* p, float r0, float r1, bool has1,
                                            bool vec) {
     if (OUT == BS_DTYPE_F32) {
-        if (vec && has1) __stcs((float2*)p, make_float2(r0, r1));
-        else { __stcs((float*)p, r0); if (has1) __stcs((float*)p + 1, r1); }
+        if (a.swap) {
+            const unsigned int u0 = bswap32(__float_as_uint(r0)), u1 = bswap32(__float_as_uint(r1));
+            if (vec && has1) __stcs((uint2*)p, make_uint2(u0, u1));
+            else { __stcs((unsigned int*)p, u0); if (has1) __stcs((unsigned int*)p + 1, u1); }
+        } else if (vec && has1) {
+            __stcs((float2*)p, make_float2(r0, r1));
+        } else {
+            __stcs((float*)p, r0);
+            if (has1) __stcs((float*)p + 1, r1);
+        }
     } else if (OUT == BS_DTYPE_U16) {
-        const unsigned int c0 = conv_int<OUT>(a, r0), c1 = conv_int<OUT>(a, r1);
-        if (vec && has1) *(unsigned int*)p = c0 | (c1 << 16);
-        else { p[0] = (unsigned short)c0; if (has1) p[1] = (unsigned short)c1; }
+        unsigned int c = conv_int<OUT>(a, r0) | (conv_int<OUT>(a, r1) << 16);
+        if (a.swap) c = bswap16x2(c);
+        if (vec && has1) *(unsigned int*)p = c;
+        else { p[0] = (unsigned short)(c & 0xffffu); if (has1) p[1] = (unsigned short)(c >> 16); }
     } else {
         const unsigned int c0 = conv_int<OUT>(a, r0), c1 = conv_int<OUT>(a, r1);
         if (vec && has1) *(unsigned short*)p = (unsigned short)(c0 | (c1 << 8));
@@ -1277,6 +1290,7 @@ int fuse2_launch(bs_ctx* ctx, const bs_view* views, int n_views, int nb, const l
     a.hdr = (const TileHdr*)W->hdr;
     a.pool = (const ViewItem*)W->pool;
     a.use_blend = use_blend;
+    a.swap = (p->out_big_endian && bs_out_elem_size(p->out_dtype) > 1) ? 1 : 0;
     {
         const char* e = getenv("BS_FUSE_NO_XYAFF");
         a.xyaff = (xyaff && !(e && *e && *e != '0')) ? 1 : 0;
@@ -1307,6 +1321,13 @@ int fuse2_launch(bs_ctx* ctx, const bs_view* views, int n_views, int nb, const l
     return BS_OK;
 }
 
+__global__ void fuse_bswap_kernel(void* data, size_t n, int es) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        if (es == 4) ((unsigned int*)data)[i] = bswap32(((unsigned int*)data)[i]);
+        else ((unsigned short*)data)[i] = (unsigned short)bswap16x2(((unsigned short*)data)[i]);
+    }
+}
+
 int validate_blocks(bs_ctx* ctx, int nb, const long long* bmin, const long long* bsize, const bs_fuse_params* p) {
     if (!bmin || !bsize || !p) return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse: NULL argument");
     if (nb < 0) return bs_set_error(ctx, BS_ERR_ARG, "bs_fuse_blocks: n_blocks < 0");
@@ -1324,9 +1345,16 @@ int fuse_blocks_dev(bs_ctx* ctx, const bs_view* views, int n_views, int nb, cons
     if (rc) return rc;
     if (nb == 0) return BS_OK;
     if (eligible(ctx, views, n_views, p)) return fuse2_launch(ctx, views, n_views, nb, bmin, bsize, p, outs_dev);
+    const size_t es = bs_out_elem_size(p->out_dtype);
     for (int b = 0; b < nb; ++b) {
         rc = bs_fuse_legacy_block(ctx, views, n_views, bmin + 3 * b, bsize + 3 * b, p, outs_dev[b]);
         if (rc) return rc;
+        if (p->out_big_endian && es > 1) {   // the generic tile kernel stores native order: swap in place
+            const size_t n = (size_t)bsize[3 * b] * bsize[3 * b + 1] * bsize[3 * b + 2];
+            bs_launch_scope scope(ctx, "fuse_bswap");
+            fuse_bswap_kernel<<<(unsigned int)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(outs_dev[b], n, (int)es);
+            BS_CUDA(ctx, cudaGetLastError());
+        }
     }
     return BS_OK;
 }

@@ -76,14 +76,66 @@ constexpr int pick_factor(int r) {
 }
 }  // namespace cx
 
-__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+// ---------------------------------------------------------------------------- complex arithmetic
+// sm_100a has packed FP32 pairs (FADD2 / FMUL2 / FFMA2 on an aligned register pair, with per-operand half swizzles,
+// per-half negation and scalar broadcast folded into the instruction by ptxas): a complex add is ONE instruction, a
+// complex multiply three, x +- i*y one.  The FFT passes are instruction-issue bound, so every butterfly below is
+// written on these primitives.  BS_FFT_PACKED=0 keeps the scalar formulation (same values up to fma contraction).
+#ifndef BS_FFT_PACKED
+#define BS_FFT_PACKED 1
+#endif
+#if BS_FFT_PACKED
+#define BS_P2_IN(a) "f"(a.x), "f"(a.y)
+__device__ __forceinline__ float2 p_add(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; add.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : BS_P2_IN(a), BS_P2_IN(b));
+    return r;
 }
-__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 p_sub(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; sub.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : BS_P2_IN(a), BS_P2_IN(b));
+    return r;
+}
+__device__ __forceinline__ float2 p_mul(float2 a, float2 b) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rc, ra, rb; mov.b64 {%0,%1}, rc;}"
+        : "=f"(r.x), "=f"(r.y) : BS_P2_IN(a), BS_P2_IN(b));
+    return r;
+}
+__device__ __forceinline__ float2 p_fma(float2 a, float2 b, float2 c) {
+    float2 r;
+    asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mov.b64 rc, {%6,%7};"
+        " fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0,%1}, rd;}"
+        : "=f"(r.x), "=f"(r.y) : BS_P2_IN(a), BS_P2_IN(b), BS_P2_IN(c));
+    return r;
+}
+#undef BS_P2_IN
+#else
+__device__ __forceinline__ float2 p_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 p_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 p_mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+__device__ __forceinline__ float2 p_fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+__device__ __forceinline__ float2 p_swap(float2 a) { return make_float2(a.y, a.x); }
+__device__ __forceinline__ float2 p_bc(float s) { return make_float2(s, s); }
+
+// a * b = a.x * b + a.y * (i b)
+__device__ __forceinline__ float2 cmulf(float2 a, float2 b) {
+    return p_fma(p_bc(a.y), p_mul(p_swap(b), make_float2(-1.f, 1.f)), p_mul(p_bc(a.x), b));
+}
+__device__ __forceinline__ float2 caddf(float2 a, float2 b) { return p_add(a, b); }
+__device__ __forceinline__ float2 csubf(float2 a, float2 b) { return p_sub(a, b); }
+// a + s * (-i b)  and  a + s * (i b)   (s real)
+__device__ __forceinline__ float2 cadd_mi(float2 a, float2 b, float s = 1.f) { return p_fma(p_swap(b), make_float2(s, -s), a); }
+__device__ __forceinline__ float2 cadd_pi(float2 a, float2 b, float s = 1.f) { return p_fma(p_swap(b), make_float2(-s, s), a); }
+// a + s * b, s * a   (s real)
+__device__ __forceinline__ float2 caxpy(float s, float2 b, float2 a) { return p_fma(p_bc(s), b, a); }
+__device__ __forceinline__ float2 cscale(float s, float2 a) { return p_mul(p_bc(s), a); }
 // multiply by -i / +i
-__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
-__device__ __forceinline__ float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }
+__device__ __forceinline__ float2 mul_mi(float2 a) { return p_mul(p_swap(a), make_float2(1.f, -1.f)); }
+__device__ __forceinline__ float2 mul_pi(float2 a) { return p_mul(p_swap(a), make_float2(-1.f, 1.f)); }
 
 // v * W_R^T (forward twiddle e^{-2 pi i T / R}) with T, R compile-time
 template <int T, int R>
@@ -94,12 +146,12 @@ __device__ __forceinline__ float2 mul_w(float2 v) {
     } else if constexpr ((4 * t) % R == 0) {
         constexpr int q = (4 * t) / R;
         if constexpr (q == 1) return mul_mi(v);
-        else if constexpr (q == 2) return make_float2(-v.x, -v.y);
+        else if constexpr (q == 2) return p_mul(v, make_float2(-1.f, -1.f));
         else return mul_pi(v);
     } else {
         constexpr float c = (float)cx::cos2pi(t, R);
         constexpr float s = (float)(-cx::sin2pi(t, R));
-        return make_float2(v.x * c - v.y * s, v.x * s + v.y * c);
+        return p_fma(p_swap(v), make_float2(-s, s), cscale(c, v));   // (v.x c - v.y s, v.y c + v.x s)
     }
 }
 
@@ -121,34 +173,33 @@ __device__ __forceinline__ void dft(float2 (&x)[R]) {
         x[1] = csubf(a, b);
     } else if constexpr (R == 3) {
         constexpr float s = (float)cx::sin2pi(1, 3);
-        float2 t1 = caddf(x[1], x[2]);
-        float2 t2 = make_float2(x[0].x - 0.5f * t1.x, x[0].y - 0.5f * t1.y);
-        float2 d = csubf(x[1], x[2]);
-        float2 t3 = make_float2(s * d.x, s * d.y);
+        const float2 t1 = caddf(x[1], x[2]);
+        const float2 t2 = caxpy(-0.5f, t1, x[0]);
+        const float2 d = csubf(x[1], x[2]);
         x[0] = caddf(x[0], t1);
-        x[1] = caddf(t2, mul_mi(t3));
-        x[2] = caddf(t2, mul_pi(t3));
+        x[1] = cadd_mi(t2, d, s);
+        x[2] = cadd_pi(t2, d, s);
     } else if constexpr (R == 4) {
-        float2 a = caddf(x[0], x[2]), b = csubf(x[0], x[2]);
-        float2 c = caddf(x[1], x[3]), d = csubf(x[1], x[3]);
+        const float2 a = caddf(x[0], x[2]), b = csubf(x[0], x[2]);
+        const float2 c = caddf(x[1], x[3]), d = csubf(x[1], x[3]);
         x[0] = caddf(a, c);
         x[2] = csubf(a, c);
-        x[1] = caddf(b, mul_mi(d));
-        x[3] = caddf(b, mul_pi(d));
+        x[1] = cadd_mi(b, d);
+        x[3] = cadd_pi(b, d);
     } else if constexpr (R == 5) {
         constexpr float c1 = (float)cx::cos2pi(1, 5), c2 = (float)cx::cos2pi(2, 5);
         constexpr float s1 = (float)cx::sin2pi(1, 5), s2 = (float)cx::sin2pi(2, 5);
-        float2 t1 = caddf(x[1], x[4]), t2 = caddf(x[2], x[3]);
-        float2 t3 = csubf(x[1], x[4]), t4 = csubf(x[2], x[3]);
-        float2 a1 = make_float2(x[0].x + c1 * t1.x + c2 * t2.x, x[0].y + c1 * t1.y + c2 * t2.y);
-        float2 a2 = make_float2(x[0].x + c2 * t1.x + c1 * t2.x, x[0].y + c2 * t1.y + c1 * t2.y);
-        float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
-        float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+        const float2 t1 = caddf(x[1], x[4]), t2 = caddf(x[2], x[3]);
+        const float2 t3 = csubf(x[1], x[4]), t4 = csubf(x[2], x[3]);
+        const float2 a1 = caxpy(c2, t2, caxpy(c1, t1, x[0]));
+        const float2 a2 = caxpy(c1, t2, caxpy(c2, t1, x[0]));
+        const float2 b1 = caxpy(s2, t4, cscale(s1, t3));
+        const float2 b2 = caxpy(-s1, t4, cscale(s2, t3));
         x[0] = caddf(x[0], caddf(t1, t2));
-        x[1] = caddf(a1, mul_mi(b1));
-        x[4] = caddf(a1, mul_pi(b1));
-        x[2] = caddf(a2, mul_mi(b2));
-        x[3] = caddf(a2, mul_pi(b2));
+        x[1] = cadd_mi(a1, b1);
+        x[4] = cadd_pi(a1, b1);
+        x[2] = cadd_mi(a2, b2);
+        x[3] = cadd_pi(a2, b2);
     } else {
         // Cooley-Tukey in registers: n = B*n1 + n2, k = k1 + A*k2
         constexpr int A = cx::pick_factor(R);

@@ -109,7 +109,7 @@ class N5Store:
         """block: [z, y, x] array (x fastest), at most blockSize in every dimension."""
         a = self.dataset_attributes(path)
         dt = np.dtype(_DTYPES[a["dataType"]])
-        if block.dtype != dt:
+        if block.dtype.newbyteorder("=") != dt:      # big-endian blocks (swapped on the device) pass through as they are
             raise ValueError(f"block dtype {block.dtype} != dataset dtype {dt}")
         dims_xyz = block.shape[::-1]
         header = struct.pack(">HH", 0, len(dims_xyz)) + b"".join(struct.pack(">I", int(d)) for d in dims_xyz)

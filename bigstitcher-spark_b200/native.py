@@ -70,9 +70,16 @@ class PcmJobC(C.Structure):
                 ("min2", C.c_longlong * 3), ("dims", C.c_longlong * 3)]
 
 
+def _out_dtype(params):
+    """numpy dtype of a fused block: byte order follows params.out_big_endian (the bytes are what the device wrote)."""
+    dt = np.dtype(_BS2NP[params.out_dtype])
+    return dt.newbyteorder(">") if getattr(params, "out_big_endian", 0) and dt.itemsize > 1 else dt
+
+
 class FuseParamsC(C.Structure):
     _fields_ = [("fusion_type", C.c_int), ("interpolation", C.c_int), ("out_dtype", C.c_int),
-                ("blend_lut_n", C.c_int), ("min_intensity", C.c_double), ("max_intensity", C.c_double)]
+                ("blend_lut_n", C.c_int), ("min_intensity", C.c_double), ("max_intensity", C.c_double),
+                ("out_big_endian", C.c_int), ("reserved", C.c_int)]
 
 
 @dataclass
@@ -409,7 +416,7 @@ class Context:
 
     @staticmethod
     def fuse_params(fusion_type=FUSE_AVG_BLEND, interpolation=1, out_dtype=DTYPE_F32, blend_lut_n=0,
-                    min_intensity=0.0, max_intensity=65535.0):
+                    min_intensity=0.0, max_intensity=65535.0, out_big_endian=False):
         p = FuseParamsC()
         p.fusion_type = FUSION_TYPES[fusion_type] if isinstance(fusion_type, str) else int(fusion_type)
         p.interpolation = int(interpolation)
@@ -417,6 +424,7 @@ class Context:
         p.blend_lut_n = int(blend_lut_n)
         p.min_intensity = float(min_intensity)
         p.max_intensity = float(max_intensity)
+        p.out_big_endian = 1 if out_big_endian else 0
         return p
 
     @staticmethod
@@ -443,7 +451,7 @@ class Context:
         bmin = (C.c_longlong * 3)(*[int(v) for v in block_min_xyz])
         bsz = (C.c_longlong * 3)(*[int(v) for v in block_size_xyz])
         if out is None:
-            out = np.empty(tuple(int(v) for v in block_size_xyz)[::-1], dtype=_BS2NP[params.out_dtype])
+            out = np.empty(tuple(int(v) for v in block_size_xyz)[::-1], dtype=_out_dtype(params))
         p, on_dev, _ = _ptr_of(out)
         self._check(self.lib.bs_fuse_block(self.h, arr, n, bmin, bsz, C.byref(params), p, 1 if on_dev else 0))
         return out
@@ -460,7 +468,7 @@ class Context:
             bmin[3 * i:3 * i + 3] = [int(v) for v in block_mins_xyz[i]]
             bsz[3 * i:3 * i + 3] = [int(v) for v in block_sizes_xyz[i]]
         if outs is None:
-            outs = [np.empty(tuple(int(v) for v in s)[::-1], dtype=_BS2NP[params.out_dtype]) for s in block_sizes_xyz]
+            outs = [np.empty(tuple(int(v) for v in s)[::-1], dtype=_out_dtype(params)) for s in block_sizes_xyz]
         ptrs = (C.c_void_p * max(nb, 1))()
         on_dev = None
         keep = []

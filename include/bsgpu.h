@@ -158,6 +158,9 @@ typedef struct {
     int    blend_lut_n;     /* 0: analytic cosine; n>0: n-segment linear-interpolated cosine table */
     double min_intensity;   /* converter range for integer outputs */
     double max_intensity;
+    int    out_big_endian;  /* 1: 2- and 4-byte output elements leave the device byte-swapped, i.e. as the big-endian
+                             * payload of an N5 block (DefaultBlockWriter), so the host writes the bytes as they come */
+    int    reserved;
 } bs_fuse_params;
 
 void bs_fuse_default_params(bs_fuse_params* p);

@@ -102,16 +102,17 @@ std::vector<bs_view> unpack_views(JNIEnv* env, jint n, jdoubleArray models, jlon
     return v;
 }
 
-// iparams = {fusionType, interpolation, outDtype, blendLutN}; dparams = {minIntensity, maxIntensity}
+// iparams = {fusionType, interpolation, outDtype, blendLutN, outBigEndian}; dparams = {minIntensity, maxIntensity}
 bs_fuse_params fuse_params(JNIEnv* env, jintArray iparams, jdoubleArray dparams) {
-    jint ip[4];
+    jint ip[5];
     jdouble dp[2];
-    env->GetIntArrayRegion(iparams, 0, 4, ip);
+    env->GetIntArrayRegion(iparams, 0, 5, ip);
     env->GetDoubleArrayRegion(dparams, 0, 2, dp);
     bs_fuse_params p;
     bs_fuse_default_params(&p);
     p.fusion_type = ip[0]; p.interpolation = ip[1]; p.out_dtype = ip[2]; p.blend_lut_n = ip[3];
     p.min_intensity = dp[0]; p.max_intensity = dp[1];
+    p.out_big_endian = ip[4];
     return p;
 }
 

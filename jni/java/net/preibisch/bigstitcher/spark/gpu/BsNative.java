@@ -55,7 +55,7 @@ public final class BsNative
 	public static native long[] pcmDebugPcm( long ctx, Object img1, Object img2, long[] dims, int dtype, int[] extension, Object outPcm );
 
 	/** models n*12, handles n*{volume, content}, blend n*{border[3], range[3]}, windows n*{fullDims[3], windowMin[3]} or null;
-	 *  iparams {fusionType, interpolation, outDtype, blendLutN}; dparams {minIntensity, maxIntensity} */
+	 *  iparams {fusionType, interpolation, outDtype, blendLutN, outBigEndian (1: N5 block payload byte order)}; dparams {minIntensity, maxIntensity} */
 	public static native void fuseBlock( long ctx, int nViews, double[] models, long[] handles, float[] blend, long[] windows,
 			long[] blockMin, long[] blockSize, int[] iparams, double[] dparams, Object dest );
 	public static native void fuseBlocks( long ctx, int nViews, double[] models, long[] handles, float[] blend, long[] windows,

@@ -27,7 +27,7 @@ public class GpuBlockSupplier< T extends RealType< T > & NativeType< T > > imple
 	private final long[] handles;    // n * {volume, content}
 	private final float[] blend;     // n * {border[3], range[3]}
 	private final long[] windows;    // n * {fullDims[3], windowMin[3]} or null
-	private final int[] iparams;     // {fusionType, interpolation, outDtype, blendLutN}
+	private final int[] iparams;     // {fusionType, interpolation, outDtype, blendLutN, outBigEndian}
 	private final double[] dparams;  // {minIntensity, maxIntensity}
 
 	public GpuBlockSupplier( final long ctx, final T type, final long[] bbMin, final List< AffineTransform3D > srcToWorld,
@@ -44,7 +44,7 @@ public class GpuBlockSupplier< T extends RealType< T > & NativeType< T > > imple
 		this.handles = handles;
 		this.blend = blend;
 		this.windows = windows;
-		this.iparams = new int[] { fusionType, 1, outDtype, 0 };
+		this.iparams = new int[] { fusionType, 1, outDtype, 0, 0 };   // little-endian: the block goes into an ArrayImg
 		this.dparams = new double[] { minIntensity, maxIntensity };
 	}
 

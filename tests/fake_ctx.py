@@ -72,8 +72,10 @@ class FakeContext:
     # -- hot path 2
     @staticmethod
     def fuse_params(fusion_type="AVG_BLEND", interpolation=1, out_dtype=1, blend_lut_n=0, min_intensity=0.0,
-                    max_intensity=65535.0):
-        return _FuseParams(fusion_type, interpolation, out_dtype, blend_lut_n, min_intensity, max_intensity)
+                    max_intensity=65535.0, out_big_endian=False):
+        p = _FuseParams(fusion_type, interpolation, out_dtype, blend_lut_n, min_intensity, max_intensity)
+        p.out_big_endian = bool(out_big_endian)
+        return p
 
     def _views(self, views):
         out = []
@@ -104,6 +106,8 @@ class FakeContext:
 
     def fuse_blocks(self, views, block_mins, block_sizes, params=None, outs=None):
         res = [self.fuse_block(views, mn, sz, params) for mn, sz in zip(block_mins, block_sizes)]
+        if getattr(params, "out_big_endian", False):      # the device hands back big-endian payloads
+            res = [r.astype(r.dtype.newbyteorder(">")) if r.dtype.itemsize > 1 else r for r in res]
         if outs is not None:
             for o, r in zip(outs, res):
                 o[...] = r

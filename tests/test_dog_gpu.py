@@ -1,5 +1,5 @@
 """GPU parity, next row 8f-4: bs_dog_detect (through the C ABI) against oracle/dog_oracle.py.
-Bars: the SAME set of extremum voxels (integer, bit-identical); sub-pixel location within 1e-3 px; value 1e-4 relative."""
+Bars: the SAME set of extremum voxels (integer, bit-identical); sub-pixel location within 1e-3 px; value 1e-4 relative + 2e-6 (float32 DoG of a unit-range image)."""
 import numpy as np
 import pytest
 
@@ -15,7 +15,8 @@ def _compare(got, want, loc_tol=1e-3):
     for g, w in zip(got, want):
         assert g[3] == w[3]
         assert np.allclose(g[0], w[0], atol=loc_tol), (g, w)
-        assert abs(g[1] - w[1]) <= 1e-4 * max(abs(w[1]), 1e-3)
+        # the DoG is a float32 difference of two blurs of a [0, 1] image scaled by 1 / (k - 1) = 5.3: absolute floor 2e-6
+        assert abs(g[1] - w[1]) <= 1e-4 * abs(w[1]) + 2e-6
 
 
 @pytest.mark.parametrize("interval", [((0, 0, 0), (56, 48, 40)), ((10, 8, 4), (30, 32, 28)), ((28, 24, 0), (28, 24, 40))])

@@ -4,6 +4,7 @@ outputs within 1 grey level where the float result sits on a rounding boundary."
 import numpy as np
 import pytest
 
+import bsgpu
 from oracle import fusion_oracle as fo
 from tests import synth
 
@@ -416,5 +417,28 @@ def test_xy_affine_path_equals_generic_path(ctx, monkeypatch):
     assert np.count_nonzero(a) > 0.6 * a.size
     err = np.abs(a - b) / np.maximum(np.abs(b), 250.0)
     assert err.max() < 2e-5
+    for h in handles:
+        ctx.volume_free(h)
+
+
+@pytest.mark.parametrize("out_dtype", ["float32", "uint16", "uint8"])
+@pytest.mark.parametrize("ft,rot", [("AVG_BLEND", 0.0), ("AVG_BLEND", 0.4), ("MAX_INTENSITY", 0.0)])
+def test_big_endian_output_is_the_byte_swapped_block(ctx, out_dtype, ft, rot):
+    """bs_fuse_params.out_big_endian: the block leaves the device as an N5 payload (translation kernel, general
+    kernel and the generic tile kernel + swap pass), odd sizes so the scalar and the paired stores both run."""
+    views = _scene(seed=35, n=3, shape=(40, 48, 56), rot=rot)
+    handles = [ctx.volume_upload(v) for v, _ in views]
+    gv = []
+    for (vol, M), h in zip(views, handles):
+        border, rng = fo.adjust_blending(M)
+        gv.append(dict(src_to_world=M, vol_handle=h, blend_border=border, blend_range=rng))
+    dt = {"float32": bsgpu.native.DTYPE_F32, "uint16": bsgpu.native.DTYPE_U16, "uint8": bsgpu.native.DTYPE_U8}[out_dtype]
+    mins, sizes = [(1, 0, 0), (40, 3, 2)], [(71, 33, 17), (64, 16, 8)]
+    le = ctx.fuse_blocks(gv, mins, sizes, ctx.fuse_params(ft, 1, dt, 0, 0.0, 4000.0))
+    be = ctx.fuse_blocks(gv, mins, sizes, ctx.fuse_params(ft, 1, dt, 0, 0.0, 4000.0, out_big_endian=True))
+    for a, b in zip(le, be):
+        assert a.any()
+        assert b.dtype.byteorder in (">", "|") and np.array_equal(a, b.astype(a.dtype))
+        assert a.tobytes() == b.byteswap().tobytes()
     for h in handles:
         ctx.volume_free(h)
