@@ -130,6 +130,7 @@ void bs_destroy(bs_ctx* ctx) {
     }
     bs_pcm_workspace_free(ctx);
     bs_fuse2_free(ctx);
+    bs_dog_free(ctx);
     bs_comm_free(ctx);
     if (ctx->fuse_ring_dev) cudaFree(ctx->fuse_ring_dev);
     if (ctx->fuse_ring_host) cudaFreeHost(ctx->fuse_ring_host);

@@ -86,6 +86,7 @@ struct bs_ctx {
     void* fuse_out = nullptr;         // device staging for host outputs
     size_t fuse_out_cap = 0;
     void* fuse2 = nullptr;            // fuse_tma.cu workspace (Fuse2Ws)
+    void* dog = nullptr;              // dog.cu workspace (region buffers, detection list)
     void* nccl_comm = nullptr;        // comm.cu: ncclComm_t of the view-sharded exchange (bs_comm_init)
     int nccl_ranks = 0;
     // recycled device buffers of async-uploaded volumes, keyed by byte size
@@ -138,6 +139,7 @@ int bs_volume_acquire(bs_ctx* ctx, bs_volume& v);
 void bs_pcm_workspace_free(bs_ctx* ctx);
 // fuse_tma.cu
 void bs_fuse2_free(bs_ctx* ctx);
+void bs_dog_free(bs_ctx* ctx);
 // comm.cu
 void bs_comm_free(bs_ctx* ctx);
 // fuse.cu: generic tile kernel for one block into a device buffer (ctx->mu held by the caller)

@@ -101,6 +101,122 @@ __global__ void __launch_bounds__(256) k_dog_blur(const __grid_constant__ BlurAr
     }
 }
 
+// ------------------------------------------------------------------------------------------ sliding-window blur
+// The same sums as k_dog_blur (symmetric pairs, outermost tap first, so results are bit-identical), but every thread
+// produces DOG_CH consecutive outputs along the blur axis from a register window of DOG_CH + 2 R inputs: ~2.5 loads
+// per output instead of 2 (2 r + 1).  Half kernels are zero-padded to the compile-time radius R (a zero tap adds an
+// exact +0).  x pass: the region's row pitch is a multiple of 4 floats, windows are fetched as aligned float4;
+// y / z passes: lanes run along x (coalesced rows).
+#define DOG_CH 8
+#define DOG_WIN_MAXR 12
+struct BlurWinArgs {
+    const float* in_a;
+    const float* in_b;
+    float* out_a;
+    float* out_b;
+    int dims[3];            // dims[0] is the padded row pitch (multiple of 8)
+    float scale;
+    float ka[DOG_WIN_MAXR + 1], kb[DOG_WIN_MAXR + 1];   // ka[t]: coefficient at distance t, zero beyond the real radius
+};
+
+template <int R, int W>
+__device__ __forceinline__ float dog_win_sum(const float (&w)[W], const float* __restrict__ k, int c) {
+    float s = 0.f;
+#pragma unroll
+    for (int t = R; t >= 1; --t) s = fmaf(k[t], w[c - t] + w[c + t], s);
+    return fmaf(k[0], w[c], s);
+}
+
+// x pass: in_a == in_b (the loaded region); one thread = 8 consecutive x of one row
+template <int R>
+__global__ void __launch_bounds__(256) k_dog_blur_x(const __grid_constant__ BlurWinArgs a) {
+    constexpr int WL = (R + 3) & ~3;               // window reach rounded up to whole float4
+    constexpr int W = DOG_CH + 2 * WL;
+    const int pitch = a.dims[0], nch = pitch / DOG_CH;
+    const long long items = (long long)nch * a.dims[1] * a.dims[2];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+        const int cx = (int)(i % nch);
+        const long long row = i / nch;
+        const float* src = a.in_a + row * pitch;
+        const int x0 = cx * DOG_CH;
+        float w[W];
+#pragma unroll
+        for (int q = 0; q < W / 4; ++q) {
+            const int xs = x0 - WL + 4 * q;
+            if (xs >= 0 && xs + 3 < pitch) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(src + xs));
+                w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) w[4 * q + e] = __ldg(src + min(max(xs + e, 0), pitch - 1));
+            }
+        }
+        float ra[DOG_CH], rb[DOG_CH];
+#pragma unroll
+        for (int o = 0; o < DOG_CH; ++o) {
+            ra[o] = dog_win_sum<R, W>(w, a.ka, WL + o);
+            rb[o] = dog_win_sum<R, W>(w, a.kb, WL + o);
+        }
+        float4* oa = reinterpret_cast<float4*>(a.out_a + row * pitch + x0);
+        float4* ob = reinterpret_cast<float4*>(a.out_b + row * pitch + x0);
+        oa[0] = make_float4(ra[0], ra[1], ra[2], ra[3]); oa[1] = make_float4(ra[4], ra[5], ra[6], ra[7]);
+        ob[0] = make_float4(rb[0], rb[1], rb[2], rb[3]); ob[1] = make_float4(rb[4], rb[5], rb[6], rb[7]);
+    }
+}
+
+// y (AXIS 1) and z (AXIS 2) passes; LAST writes the DoG (A - B) * scale
+template <int R, int AXIS, bool LAST>
+__global__ void __launch_bounds__(256) k_dog_blur_yz(const __grid_constant__ BlurWinArgs a) {
+    constexpr int W = DOG_CH + 2 * R;
+    const int pitch = a.dims[0], len = a.dims[AXIS];
+    const int nch = (len + DOG_CH - 1) / DOG_CH;
+    const int other = AXIS == 1 ? a.dims[2] : a.dims[1];
+    const long long stride = AXIS == 1 ? pitch : (long long)pitch * a.dims[1];
+    const long long ostride = AXIS == 1 ? (long long)pitch * a.dims[1] : pitch;   // stride of the remaining axis
+    const long long items = (long long)pitch * nch * other;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % pitch);
+        const long long r = i / pitch;
+        const int c = (int)(r % nch), o2 = (int)(r / nch);
+        const int p0 = c * DOG_CH;
+        const long long base = (long long)o2 * ostride + x;
+        float wa[W], wb[W];
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            const long long q = base + (long long)min(max(p0 - R + j, 0), len - 1) * stride;
+            wa[j] = __ldg(a.in_a + q);
+            wb[j] = __ldg(a.in_b + q);
+        }
+#pragma unroll
+        for (int o = 0; o < DOG_CH; ++o) {
+            if (p0 + o >= len) break;
+            const float sa = dog_win_sum<R, W>(wa, a.ka, R + o), sb = dog_win_sum<R, W>(wb, a.kb, R + o);
+            const long long q = base + (long long)(p0 + o) * stride;
+            if (LAST) a.out_a[q] = (sa - sb) * a.scale;
+            else { a.out_a[q] = sa; a.out_b[q] = sb; }
+        }
+    }
+}
+
+template <int R>
+void dog_blur_windowed(bs_ctx* ctx, BlurWinArgs b, float* r0, float* r1, float* r2, float* r3, int blocks) {
+    // x: r0 -> (r1, r2); y: (r1, r2) -> (r3, r0); z: (r3, r0) -> r1 = DoG
+    b.in_a = r0; b.in_b = r0; b.out_a = r1; b.out_b = r2;
+    { bs_launch_scope sc(ctx, "dog_blur"); k_dog_blur_x<R><<<blocks, 256, 0, ctx->stream>>>(b); }
+    b.in_a = r1; b.in_b = r2; b.out_a = r3; b.out_b = r0;
+    { bs_launch_scope sc(ctx, "dog_blur"); k_dog_blur_yz<R, 1, false><<<blocks, 256, 0, ctx->stream>>>(b); }
+    b.in_a = r3; b.in_b = r0; b.out_a = r1; b.out_b = nullptr;
+    { bs_launch_scope sc(ctx, "dog_blur"); k_dog_blur_yz<R, 2, true><<<blocks, 256, 0, ctx->stream>>>(b); }
+}
+
+struct DogWs {
+    void* buf[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t cap[4] = {0, 0, 0, 0};
+    void* pts = nullptr;
+    size_t pts_cap = 0;
+    int* count = nullptr;
+};
+
 struct ExtremaArgs {
     const float* dog;       // region volume
     int rdims[3];
@@ -255,27 +371,24 @@ int bs_dog_detect(bs_ctx* ctx, unsigned long long vol_handle, const long long in
         rdims[d] = (int)rd;
         nreg *= rd;
     }
-    float *r0 = nullptr, *r1 = nullptr, *r2 = nullptr, *r3 = nullptr;
-    bs_dog_point* dpts = nullptr;
-    int* dcount = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(r0); cudaFree(r1); cudaFree(r2); cudaFree(r3); cudaFree(dpts); cudaFree(dcount);
-    };
-#define DOG_CUDA(call)                                                                                           \
-    do {                                                                                                         \
-        cudaError_t e__ = (call);                                                                                \
-        if (e__ != cudaSuccess) {                                                                                \
-            cleanup();                                                                                           \
-            return bs_set_error(ctx, e__ == cudaErrorMemoryAllocation ? BS_ERR_NOMEM : BS_ERR_CUDA, "%s failed: %s", \
-                                #call, cudaGetErrorString(e__));                                                 \
-        }                                                                                                        \
-    } while (0)
-    DOG_CUDA(cudaMalloc(&r0, sizeof(float) * nreg));
-    DOG_CUDA(cudaMalloc(&r1, sizeof(float) * nreg));
-    DOG_CUDA(cudaMalloc(&r2, sizeof(float) * nreg));
-    DOG_CUDA(cudaMalloc(&r3, sizeof(float) * nreg));
-    DOG_CUDA(cudaMalloc(&dpts, sizeof(bs_dog_point) * (size_t)std::max(1, max_points)));
-    DOG_CUDA(cudaMalloc(&dcount, sizeof(int)));
+    // the region's rows are padded to a multiple of 8 floats (more halo on the right: the extra columns hold real
+    // mirror-extended image data, so every used voxel is unchanged) -> aligned float4 windows in the x pass
+    nreg = nreg / rdims[0];
+    rdims[0] = (rdims[0] + 7) & ~7;
+    nreg *= rdims[0];
+    if (!ctx->dog) ctx->dog = new DogWs();
+    DogWs* W = (DogWs*)ctx->dog;
+    for (int i = 0; i < 4; ++i) {
+        rc = bs_ensure_dev(ctx, &W->buf[i], &W->cap[i], sizeof(float) * (size_t)nreg);
+        if (rc) return rc;
+    }
+    rc = bs_ensure_dev(ctx, &W->pts, &W->pts_cap, sizeof(bs_dog_point) * (size_t)std::max(1, max_points));
+    if (rc) return rc;
+    if (!W->count) BS_CUDA(ctx, cudaMalloc(&W->count, sizeof(int)));
+    float *r0 = (float*)W->buf[0], *r1 = (float*)W->buf[1], *r2 = (float*)W->buf[2], *r3 = (float*)W->buf[3];
+    bs_dog_point* dpts = (bs_dog_point*)W->pts;
+    int* dcount = W->count;
+#define DOG_CUDA(call) BS_CUDA(ctx, call)
     DOG_CUDA(cudaMemsetAsync(dcount, 0, sizeof(int), ctx->stream));
     const int blocks = (int)std::min<long long>((nreg + 255) / 256, (long long)ctx->sm_count * 32);
     {
@@ -289,23 +402,37 @@ int bs_dog_detect(bs_ctx* ctx, unsigned long long vol_handle, const long long in
         k_dog_load<<<blocks, 256, 0, ctx->stream>>>(a);
     }
     DOG_CUDA(cudaGetLastError());
-    BlurArgs b;
-    memset(&b, 0, sizeof(b));
-    for (int d = 0; d < 3; ++d) b.dims[d] = rdims[d];
-    b.ra = ra; b.rb = rb;
-    memcpy(b.ka, ka.data(), sizeof(float) * ka.size());
-    memcpy(b.kb, kb.data(), sizeof(float) * kb.size());
-    b.scale = (float)(1.0 / (k - 1.0));           // K_MIN1_INV
-    // x: r0 -> (r1, r2); y: (r1, r2) -> (r3, r0); z: (r3, r0) -> r1 = DoG
-    const float* ina[3] = {r0, r1, r3};
-    const float* inb[3] = {r0, r2, r0};
-    float* outa[3] = {r1, r3, r1};
-    float* outb[3] = {r2, r0, nullptr};
-    for (int axis = 0; axis < 3; ++axis) {
-        b.in_a = ina[axis]; b.in_b = inb[axis]; b.out_a = outa[axis]; b.out_b = outb[axis]; b.axis = axis;
-        bs_launch_scope sc(ctx, "dog_blur");
-        k_dog_blur<<<blocks, 256, 0, ctx->stream>>>(b);
+    const float dog_scale = (float)(1.0 / (k - 1.0));           // K_MIN1_INV
+    if (rb <= DOG_WIN_MAXR) {
+        BlurWinArgs b;
+        memset(&b, 0, sizeof(b));
+        for (int d = 0; d < 3; ++d) b.dims[d] = rdims[d];
+        b.scale = dog_scale;
+        for (int t = 0; t <= ra; ++t) b.ka[t] = ka[(size_t)(ra + t)];
+        for (int t = 0; t <= rb; ++t) b.kb[t] = kb[(size_t)(rb + t)];
+        const int wblocks = (int)std::min<long long>((nreg / DOG_CH + 255) / 256 + 1, (long long)ctx->sm_count * 32);
+        if (rb <= 6) dog_blur_windowed<6>(ctx, b, r0, r1, r2, r3, wblocks);
+        else dog_blur_windowed<12>(ctx, b, r0, r1, r2, r3, wblocks);
         DOG_CUDA(cudaGetLastError());
+    } else {
+        BlurArgs b;
+        memset(&b, 0, sizeof(b));
+        for (int d = 0; d < 3; ++d) b.dims[d] = rdims[d];
+        b.ra = ra; b.rb = rb;
+        memcpy(b.ka, ka.data(), sizeof(float) * ka.size());
+        memcpy(b.kb, kb.data(), sizeof(float) * kb.size());
+        b.scale = dog_scale;
+        // x: r0 -> (r1, r2); y: (r1, r2) -> (r3, r0); z: (r3, r0) -> r1 = DoG
+        const float* ina[3] = {r0, r1, r3};
+        const float* inb[3] = {r0, r2, r0};
+        float* outa[3] = {r1, r3, r1};
+        float* outb[3] = {r2, r0, nullptr};
+        for (int axis = 0; axis < 3; ++axis) {
+            b.in_a = ina[axis]; b.in_b = inb[axis]; b.out_a = outa[axis]; b.out_b = outb[axis]; b.axis = axis;
+            bs_launch_scope sc(ctx, "dog_blur");
+            k_dog_blur<<<blocks, 256, 0, ctx->stream>>>(b);
+            DOG_CUDA(cudaGetLastError());
+        }
     }
     {
         ExtremaArgs a;
@@ -338,9 +465,19 @@ int bs_dog_detect(bs_ctx* ctx, unsigned long long vol_handle, const long long in
         });
     }
 #undef DOG_CUDA
-    cleanup();
     *n_found = n;      // > max_points: the caller's buffer was too small, the first max_points (unsorted subset) were kept
     return BS_OK;
 }
 
 }  // extern "C"
+
+void bs_dog_free(bs_ctx* ctx) {
+    DogWs* W = (DogWs*)ctx->dog;
+    if (!W) return;
+    for (int i = 0; i < 4; ++i)
+        if (W->buf[i]) cudaFree(W->buf[i]);
+    if (W->pts) cudaFree(W->pts);
+    if (W->count) cudaFree(W->count);
+    delete W;
+    ctx->dog = nullptr;
+}

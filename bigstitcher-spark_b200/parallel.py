@@ -11,6 +11,34 @@ from __future__ import annotations
 import math
 
 
+def bind_to_gpu_numa_node(device: int):
+    """Pin this process (one per GPU) to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is
+    allocated: first-touch then places the staging buffers next to the GPU's PCIe root, so eight ranks streaming tiles
+    and fused blocks do not all cross the socket interconnect.  Returns the node (or None when the platform does not
+    say: no sysfs entry, node -1, cpuset forbids it)."""
+    import os
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
 def shard_range(n: int, rank: int, world: int):
     """Contiguous, balanced [lo, hi) of n items for this rank."""
     base, rem = divmod(n, world)

@@ -168,3 +168,27 @@ def test_zstd_codec_both_back_ends_and_n5_zarr_blocks(tmp_path):
     assert zs.array_meta("0")["compressor"] == {"id": "zstd", "level": 3}
     assert np.array_equal(zs.read_volume("0"), vol)
     assert np.array_equal(zs.read_region("0", (10, -3, 5), (30, 20, 40)), want)
+
+
+def test_n5_block_accepts_device_swapped_payload(tmp_path):
+    """A block that left the device big-endian (bs_fuse_params.out_big_endian) is written as it is: same file bytes
+    as the native-order block, and it reads back as the same values."""
+    from bsgpu import n5 as bn5
+    rng = np.random.default_rng(3)
+    for dt in (np.uint16, np.float32):
+        blk = (rng.random((5, 6, 7)) * 1000).astype(dt)
+        a = bn5.N5Store(str(tmp_path / f"a_{np.dtype(dt).name}.n5"), create=True)
+        b = bn5.N5Store(str(tmp_path / f"b_{np.dtype(dt).name}.n5"), create=True)
+        for st in (a, b):
+            st.create_dataset("d", (7, 6, 5), (8, 8, 8), np.dtype(dt).name, "raw")
+        a.write_block("d", (0, 0, 0), blk)
+        b.write_block("d", (0, 0, 0), blk.astype(np.dtype(dt).newbyteorder(">")))
+        fa = open(os.path.join(a.root, "d", "0", "0", "0"), "rb").read()
+        fb = open(os.path.join(b.root, "d", "0", "0", "0"), "rb").read()
+        assert fa == fb
+        assert np.array_equal(b.read_block("d", (0, 0, 0)), blk)
+
+
+def test_numa_binding_is_a_no_op_without_a_gpu():
+    from bsgpu import parallel
+    assert parallel.bind_to_gpu_numa_node(0) is None or isinstance(parallel.bind_to_gpu_numa_node(0), int)
