@@ -206,8 +206,10 @@ def _source_window(src_to_world, level_dims, wmin, wmax, margin=3):
 
 
 def affine_fusion(out_path, ctx: Context, fusion_type="AVG_BLEND", block_scale=(2, 2, 1), channel=None, timepoint=None,
-                  retries=5, blocks_per_call=16, interpolation=1, shard=(0, 1), barrier=None):
-    """`./affine-fusion -o fused.zarr [-f AVG_BLEND] [--blockScale 2,2,1] [-c channelIndex] [-t timepointIndex]`:
+                  retries=5, blocks_per_call=16, interpolation=1, shard=(0, 1), barrier=None, masks=False,
+                  mask_offset=(0.0, 0.0, 0.0)):
+    """`./affine-fusion -o fused.zarr [-f AVG_BLEND] [--blockScale 2,2,1] [-c channelIndex] [-t timepointIndex]
+    [--masks [--maskOffset x,y,z]]`:
     read the container metadata and, for every (channel, timepoint) volume (J/SparkAffineFusion.java:425-440), fuse
     its views super-block by super-block on the device, write the blocks with N5Utils.saveBlock semantics and build
     the multi-resolution pyramid (:703-782).  Returns the list of s0 datasets written.
@@ -216,6 +218,10 @@ def affine_fusion(out_path, ctx: Context, fusion_type="AVG_BLEND", block_scale=(
     133-161): the super-block grid is walked in z-slabs; for every slab only the source WINDOW of each overlapping
     view is read from its container -- at the mipmap level ViewUtil's best-resolution rule picks
     (J/util/ViewUtil.java:425-493) -- uploaded as a windowed view and freed after the slab.
+
+    ``masks``: save only the coverage masks (J/SparkAffineFusion.java:564-578, GenerateComputeBlockMasks): no image
+    data is read, a voxel is 255 / 65535 / 1.0 where any view's pixel grid (grown by ``mask_offset`` source pixels)
+    covers it; the pyramid is then built from that s0 as usual.
 
     Multi-GPU ("one N5 block-grid slab per device"): rank r of w (``shard``) fuses a contiguous run of
     z-slabs, no data-path collective; ``barrier()`` separates s0 from the pyramid levels that re-read it."""
@@ -241,13 +247,14 @@ def affine_fusion(out_path, ctx: Context, fusion_type="AVG_BLEND", block_scale=(
             done.add((ci, ti))
             levels = meta["mr_infos"][0 if is_zarr else ci + ti * nc]
             _fuse_volume_blockwise(ctx, data, src, _Sink(store, is_zarr, ci, ti), meta, levels, data.views_of(ci, ti),
-                                   fusion_type, interpolation, block_scale, retries, blocks_per_call, shard, barrier)
+                                   fusion_type, interpolation, block_scale, retries, blocks_per_call, shard, barrier,
+                                   masks, mask_offset)
             written.append(levels[0]["dataset"])
     return written
 
 
 def _fuse_volume_blockwise(ctx, data, src, sink, meta, levels, view_ids, fusion_type, interpolation, block_scale,
-                           retries, blocks_per_call, shard=(0, 1), barrier=None):
+                           retries, blocks_per_call, shard=(0, 1), barrier=None, masks=False, mask_offset=(0.0, 0.0, 0.0)):
     af = meta["anisotropy_factor"] if meta["preserve_anisotropy"] else float("nan")
     regs = bf.adjust_all_transforms({v: data.model(*v) for v in view_ids}, af)
     bb_min = np.asarray(meta["bb_min"], dtype=np.int64)
@@ -263,6 +270,9 @@ def _fuse_volume_blockwise(ctx, data, src, sink, meta, levels, view_ids, fusion_
     # (N5 payloads are big-endian): the host neither re-strides nor swaps them
     chunk_params = ctx.fuse_params(ft, interpolation, od, 0, float(meta["min_intensity"] or 0.0),
                                    float(meta["max_intensity"] or 65535.0), out_big_endian=not sink.is_zarr)
+    # the fusion kernels work on 64 x 16 x 8 output tiles anchored at the block origin: storage blocks that are whole
+    # tiles (the usual 128^3 / 64^3) are packed by the device, smaller ones would leave most of every tile empty
+    pack_on_device = bs[0] % 64 == 0 and bs[1] % 16 == 0 and bs[2] % 8 == 0
 
     # ---- per view: mipmap level by the reference's rule, level volume size, source -> world of that level
     info = {}
@@ -281,7 +291,7 @@ def _fuse_volume_blockwise(ctx, data, src, sink, meta, levels, view_ids, fusion_
 
     # pyramid straight from the resident fused block when every super-block maps onto whole voxels of every level
     abs_last = [int(v) for v in levels[-1]["absoluteDownsampling"][:3]]
-    fast_pyramid = len(levels) > 1 and all(compute[d] % abs_last[d] == 0 for d in range(3))
+    fast_pyramid = len(levels) > 1 and all(compute[d] % abs_last[d] == 0 for d in range(3)) and not masks
 
     grid = bf.grid_create(dims, compute, bs)
     slabs = {}
@@ -292,6 +302,32 @@ def _fuse_volume_blockwise(ctx, data, src, sink, meta, levels, view_ids, fusion_
     per = -(-len(zs) // world)
     my_z = zs[rank * per:(rank + 1) * per]           # contiguous run of z-slabs per device
     whole = {}      # fallback residency (content weights, winner types, float sources ...): whole views, kept
+    if masks:
+        # geometry only: full-resolution registrations and view sizes (GenerateComputeBlockMasks.java:119-128)
+        fdims = {v: tuple(int(d) for d in data.setups[v[1]].size) for v in view_ids}
+        for z0 in my_z:
+            todo, attempt = list(slabs[z0]), 0
+            while todo:
+                attempt += 1
+                if attempt > retries:
+                    raise RuntimeError(f"masks: {len(todo)} block(s) still failing after {retries} attempts")
+                failed = []
+                for gb in todo:
+                    off, size, gpos = gb
+                    mn = tuple(int(v) for v in bb_min + np.asarray(off, dtype=np.int64))
+                    sz = tuple(int(v) for v in size)
+                    # the views of THIS block (OverlappingViews on the block expanded by 2, like the fusing path): a
+                    # mask offset never pulls in a view the block does not overlap
+                    vids = bf.find_overlapping_views(fdims, regs, np.asarray(mn), np.asarray(mn) + np.asarray(sz) - 1, sorted(view_ids))
+                    gviews = [dict(src_to_world=regs[v], vol_handle=0, full_dims=fdims[v]) for v in vids]
+                    try:
+                        blk = ctx.mask_blocks(gviews, [mn], [sz], mask_offset, od)[0]
+                    except native.BsError:
+                        failed.append(gb)
+                        continue
+                    sink.save(s0, blk, gpos)
+                todo = failed
+        my_z = []
     try:
         for z0 in my_z:
             blocks = slabs[z0]
@@ -336,6 +372,15 @@ def _fuse_volume_blockwise(ctx, data, src, sink, meta, levels, view_ids, fusion_
                     else:
                         for c0 in range(0, len(todo), blocks_per_call):
                             chunk = todo[c0:c0 + blocks_per_call]
+                            if not pack_on_device:       # small storage blocks: fuse super-blocks, split on the host
+                                try:
+                                    outs = _fuse_chunk(ctx, chunk, bb_min, vdims, vregs, views, params, np_dt)
+                                except native.BsError:
+                                    failed.extend(chunk)
+                                    continue
+                                for (off, size, gpos), blk in zip(chunk, outs):
+                                    sink.save(s0, blk, gpos)
+                                continue
                             cells = [cell for gb in chunk for cell in _storage_cells(gb, bs)]
                             try:
                                 outs = _fuse_chunk(ctx, cells, bb_min, vdims, vregs, views, chunk_params, np_dt)

@@ -783,3 +783,118 @@ int bs_fuse_finish(bs_ctx* ctx, const float* sum_wi_dev, const float* sum_w_dev,
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------ --masks mode
+namespace {
+#define MASK_MAX_VIEWS 64
+struct MaskArgs {
+    double inv[MASK_MAX_VIEWS][12];    // world -> source pixel
+    double lo[MASK_MAX_VIEWS][3], hi[MASK_MAX_VIEWS][3];
+    int n_views;
+    long long bmin[3];
+    int bsize[3];
+    int out_dtype, swap;
+    void* out;
+};
+
+// one thread per voxel, x fastest; double arithmetic like the reference's AffineTransform3D.applyInverse.
+// (HBM-bound on the output write; the view loop stops at the first hit.)
+__global__ void __launch_bounds__(256) k_mask_block(const __grid_constant__ MaskArgs a, int first_pass) {
+    const long long n = (long long)a.bsize[0] * a.bsize[1] * a.bsize[2];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % a.bsize[0]);
+        const long long r = i / a.bsize[0];
+        const int y = (int)(r % a.bsize[1]), z = (int)(r / a.bsize[1]);
+        const double wx = (double)(a.bmin[0] + x), wy = (double)(a.bmin[1] + y), wz = (double)(a.bmin[2] + z);
+        bool on = false;
+        for (int v = 0; v < a.n_views && !on; ++v) {
+            const double* m = a.inv[v];
+            // separately rounded products and left-to-right sums (no fma contraction), as Java evaluates them
+            const double lx = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[0], wx), __dmul_rn(m[1], wy)), __dmul_rn(m[2], wz)), m[3]);
+            const double ly = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[4], wx), __dmul_rn(m[5], wy)), __dmul_rn(m[6], wz)), m[7]);
+            const double lz = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(m[8], wx), __dmul_rn(m[9], wy)), __dmul_rn(m[10], wz)), m[11]);
+            on = !(lx < a.lo[v][0] || lx > a.hi[v][0] || ly < a.lo[v][1] || ly > a.hi[v][1] || lz < a.lo[v][2] || lz > a.hi[v][2]);
+        }
+        if (!on && !first_pass) continue;          // later view groups only ever switch voxels on
+        if (a.out_dtype == BS_DTYPE_F32) {
+            const unsigned int one = a.swap ? 0x0000803fu : 0x3f800000u;
+            ((unsigned int*)a.out)[i] = on ? one : 0u;
+        } else if (a.out_dtype == BS_DTYPE_U16) {
+            ((unsigned short*)a.out)[i] = on ? (unsigned short)0xffffu : (unsigned short)0u;
+        } else {
+            ((unsigned char*)a.out)[i] = on ? (unsigned char)255 : (unsigned char)0;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int bs_mask_blocks(bs_ctx* ctx, const bs_view* views, int n_views, int n_blocks, const long long* block_min,
+                              const long long* block_size, const double mask_offset[3], int out_dtype, int out_big_endian,
+                              void* const* outs, int out_on_device) {
+    if (!ctx) return BS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n_views < 0 || (n_views > 0 && !views) || n_blocks < 0 || !mask_offset || (n_blocks > 0 && (!block_min || !block_size || !outs)))
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_mask_blocks: bad argument");
+    if (out_dtype != BS_DTYPE_F32 && out_dtype != BS_DTYPE_U16 && out_dtype != BS_DTYPE_U8)
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_mask_blocks: bad out_dtype %d", out_dtype);
+    BS_CUDA(ctx, cudaSetDevice(ctx->device));
+    // per view: inverse registration and the grown pixel interval
+    std::vector<double> inv((size_t)std::max(n_views, 1) * 12), lo((size_t)std::max(n_views, 1) * 3), hi((size_t)std::max(n_views, 1) * 3);
+    for (int v = 0; v < n_views; ++v) {
+        long long dims[3];
+        if (views[v].full_dims[0] > 0) {
+            for (int d = 0; d < 3; ++d) dims[d] = views[v].full_dims[d];
+        } else {
+            auto it = ctx->vols.find(views[v].vol_handle);
+            if (it == ctx->vols.end()) return bs_set_error(ctx, BS_ERR_ARG, "bs_mask_blocks: view %d has neither full_dims nor a volume", v);
+            for (int d = 0; d < 3; ++d) dims[d] = it->second.dims[d];
+        }
+        if (!bs_invert34(views[v].src_to_world, &inv[(size_t)v * 12]))
+            return bs_set_error(ctx, BS_ERR_ARG, "bs_mask_blocks: view %d has a singular transform", v);
+        for (int d = 0; d < 3; ++d) {
+            lo[(size_t)v * 3 + d] = 0.0 - mask_offset[d];
+            hi[(size_t)v * 3 + d] = (double)(dims[d] - 1) + mask_offset[d];
+        }
+    }
+    const size_t es = bs_out_elem_size(out_dtype);
+    for (int b = 0; b < n_blocks; ++b) {
+        if (!outs[b]) return bs_set_error(ctx, BS_ERR_ARG, "bs_mask_blocks: outs[%d] is NULL", b);
+        long long nvox = 1;
+        for (int d = 0; d < 3; ++d) {
+            if (block_size[3 * b + d] <= 0 || block_size[3 * b + d] > 0x7fffffffLL)
+                return bs_set_error(ctx, BS_ERR_ARG, "bs_mask_blocks: bad block_size");
+            nvox *= block_size[3 * b + d];
+        }
+        void* dev = outs[b];
+        if (!out_on_device) {
+            int rc = bs_ensure_dev(ctx, &ctx->fuse_out, &ctx->fuse_out_cap, (size_t)nvox * es);
+            if (rc) return rc;
+            dev = ctx->fuse_out;
+        }
+        MaskArgs a;
+        for (int d = 0; d < 3; ++d) { a.bmin[d] = block_min[3 * b + d]; a.bsize[d] = (int)block_size[3 * b + d]; }
+        a.out_dtype = out_dtype;
+        a.swap = (out_big_endian && es > 1) ? 1 : 0;
+        a.out = dev;
+        const int grid = (int)std::min<long long>((nvox + 255) / 256, (long long)ctx->sm_count * 16);
+        // views in groups of MASK_MAX_VIEWS (kernel-parameter space); the first group also writes the zeros
+        int v0 = 0;
+        do {
+            a.n_views = std::min(n_views - v0, MASK_MAX_VIEWS);
+            for (int v = 0; v < a.n_views; ++v) {
+                memcpy(a.inv[v], &inv[(size_t)(v0 + v) * 12], sizeof(double) * 12);
+                memcpy(a.lo[v], &lo[(size_t)(v0 + v) * 3], sizeof(double) * 3);
+                memcpy(a.hi[v], &hi[(size_t)(v0 + v) * 3], sizeof(double) * 3);
+            }
+            bs_launch_scope scope(ctx, "mask");
+            k_mask_block<<<grid, 256, 0, ctx->stream>>>(a, v0 == 0 ? 1 : 0);
+            v0 += MASK_MAX_VIEWS;
+        } while (v0 < n_views);
+        BS_CUDA(ctx, cudaGetLastError());
+        if (!out_on_device) {
+            BS_CUDA(ctx, cudaMemcpyAsync(outs[b], dev, (size_t)nvox * es, cudaMemcpyDeviceToHost, ctx->stream));
+            BS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return BS_OK;
+}

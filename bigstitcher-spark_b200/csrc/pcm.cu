@@ -373,7 +373,7 @@ __device__ __forceinline__ float raw_elem(const unsigned char* row, int dtype, i
 }
 
 template <class F>
-__global__ void __launch_bounds__(PCM_THREADS) k_fft_x_r2c_w(const __grid_constant__ XWArgs t) {
+__global__ void __launch_bounds__(PCM_THREADS, 4) k_fft_x_r2c_w(const __grid_constant__ XWArgs t) {
     const XR2CArgs& a = t.x;
     const int M = F::kStatic ? F::N : a.M;
     const int Px = 2 * M;
@@ -388,13 +388,32 @@ __global__ void __launch_bounds__(PCM_THREADS) k_fft_x_r2c_w(const __grid_consta
     unsigned long long* bars =
         reinterpret_cast<unsigned long long*>(reinterpret_cast<unsigned char*>(bs_sm + Px + (size_t)NW * 2 * M) +
                                               (size_t)NW * 2 * t.row_bytes) + 2 * wid;
-    for (int i = threadIdx.x; i < Px; i += blockDim.x) tw[i] = a.tw[i];
+    constexpr int UTW = F::N / 2 + 1;        // untangle twiddles tw[0 .. M/2]
+    if constexpr (F::kSmemTw) {
+        // the Px-entry table area holds: untangle twiddles | compact per-stage tables (conflict-free reads)
+        static_assert(UTW + F::Tw::total <= 2 * F::N, "stage tables must fit the twiddle area");
+        for (int i = threadIdx.x; i < UTW; i += blockDim.x) tw[i] = a.tw[i];
+        F::Tw::build(tw + UTW, a.tw, threadIdx.x, blockDim.x);
+    } else {
+        for (int i = threadIdx.x; i < Px; i += blockDim.x) tw[i] = a.tw[i];
+    }
     if (t.use_tma && lane == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+
+    // static plan: FFT twiddles and the untangle twiddles of this lane live in registers for the whole kernel
+    typename F::Tw twr;
+    twr.init(F::kSmemTw ? tw + UTW : tw, lane);
+    constexpr bool kRegU = F::kStatic && !F::kSmemTw;
+    constexpr int UIT = F::kStatic ? (F::N / 2 + 1 + 31) / 32 : 1;
+    float2 utw[kRegU ? UIT : 1];
+    if constexpr (kRegU) {
+#pragma unroll
+        for (int i = 0; i < UIT; ++i) utw[i] = tw[min(lane + 32 * i, M)];
+    }
 
     const long long gw = (long long)blockIdx.x * NW + wid, gstride = (long long)gridDim.x * NW;
     const int e0 = a.ex;
@@ -472,17 +491,24 @@ __global__ void __launch_bounds__(PCM_THREADS) k_fft_x_r2c_w(const __grid_consta
             }
         }
         __syncwarp();
-        const float2* res = F::run(A, B, tw, a.plan, 2, lane);
+        const float2* res = F::run(A, B, tw, twr, a.plan, 2, lane);
         // untangle: X[k] and X[M-k] share E, D and the twiddle (w_{M-k} = -conj(w_k))
-        for (int k = lane; 2 * k <= M; k += 32) {
+        auto untangle = [&](int k, float2 w) {
             const float2 Zk = res[k];
-            float2 Zm = res[k == 0 ? 0 : M - k];
-            Zm.y = -Zm.y;
-            const float2 E = make_float2(0.5f * (Zk.x + Zm.x), 0.5f * (Zk.y + Zm.y));
-            const float2 D = make_float2(0.5f * (Zk.x - Zm.x), 0.5f * (Zk.y - Zm.y));
-            const float2 wD = cmulf(tw[k], D);
-            __stcg(srow + k, make_float2(E.x + wD.y, E.y - wD.x));            // E - i w D
-            if (2 * k != M) __stcg(srow + (M - k), make_float2(E.x - wD.y, -E.y - wD.x));   // conj(E) - i conj(w D)
+            const float2 Zm = p_mul(res[k == 0 ? 0 : M - k], make_float2(1.f, -1.f));   // conj
+            const float2 S = caddf(Zk, Zm), Dd = csubf(Zk, Zm);        // 2E, 2D
+            const float2 wD = cmulf(w, Dd);
+            __stcg(srow + k, cscale(0.5f, cadd_mi(S, wD)));            // E - i w D
+            if (2 * k != M) __stcg(srow + (M - k), p_mul(cadd_pi(S, wD), make_float2(0.5f, -0.5f)));   // conj(E + i w D)
+        };
+        if (F::kStatic) {
+#pragma unroll
+            for (int i = 0; i < UIT; ++i) {
+                const int k = lane + 32 * i;
+                if (2 * k <= M) untangle(k, kRegU ? utw[kRegU ? i : 0] : tw[k]);
+            }
+        } else {
+            for (int k = lane; 2 * k <= M; k += 32) untangle(k, tw[k]);
         }
         for (int k = M + 1 + lane; k < pitch; k += 32) __stcg(srow + k, make_float2(0.f, 0.f));
         __syncwarp();  // A/B and the consumed raw buffer are free again
@@ -491,7 +517,7 @@ __global__ void __launch_bounds__(PCM_THREADS) k_fft_x_r2c_w(const __grid_consta
 
 #define XW_MAXV 10   // float2 per lane covering a row of up to 32 * XW_MAXV spectrum entries
 template <class F>
-__global__ void __launch_bounds__(PCM_THREADS) k_fft_x_c2r_w(const __grid_constant__ XC2RArgs a) {
+__global__ void __launch_bounds__(PCM_THREADS, 3) k_fft_x_c2r_w(const __grid_constant__ XC2RArgs a) {
     const int M = F::kStatic ? F::N : a.M;
     const int Px = 2 * M;
     const int pitch = F::kStatic ? ((F::N + 1 + 15) / 16) * 16 : a.pitch;
@@ -502,6 +528,9 @@ __global__ void __launch_bounds__(PCM_THREADS) k_fft_x_c2r_w(const __grid_consta
     float2* B = A + (M + 1);
     for (int i = threadIdx.x; i < Px; i += blockDim.x) tw[i] = a.tw[i];
     __syncthreads();
+    typename F::Tw twr;
+    twr.init(tw, lane);
+    constexpr int UIT = F::kStatic ? (F::N / 2 + 1 + 31) / 32 : 1;
     const long long n_lines = (long long)a.Py * a.Pz;
     const long long gw = (long long)blockIdx.x * NW + wid, gstride = (long long)gridDim.x * NW;
     float2 nxt[XW_MAXV];
@@ -523,19 +552,27 @@ __global__ void __launch_bounds__(PCM_THREADS) k_fft_x_c2r_w(const __grid_consta
         }
         __syncwarp();
         if (line + gstride < n_lines) load_row(line + gstride);   // prefetch into registers
-        for (int k = lane; k < M; k += 32) {
+        // tangle: A[k] and A[M-k] share E, D and the twiddle (E' = conj E, D' = -conj D, conj w' = -w):
+        //   A[k] = conj(E + i O), A[M-k] = (E.x + O.y, E.y - O.x) with O = D conj(w_k)
+        auto tangle = [&](int k, float2 wc) {
             const float2 Xk = B[k];
-            float2 Xm = B[M - k];
-            Xm.y = -Xm.y;
-            const float2 E = make_float2(0.5f * (Xk.x + Xm.x), 0.5f * (Xk.y + Xm.y));
-            const float2 D = make_float2(0.5f * (Xk.x - Xm.x), 0.5f * (Xk.y - Xm.y));
-            float2 w = tw[k];
-            w.y = -w.y;
-            const float2 O = cmulf(D, w);
-            A[k] = make_float2(E.x - O.y, -(E.y + O.x));
+            const float2 Xm = p_mul(B[M - k], make_float2(1.f, -1.f));
+            const float2 S = caddf(Xk, Xm), Dd = csubf(Xk, Xm);       // 2E, 2D
+            const float2 O = cmulf(Dd, wc);                            // 2 O
+            A[k] = p_mul(cadd_pi(S, O), make_float2(0.5f, -0.5f));     // conj(E + i O)
+            if (k != 0 && 2 * k != M) A[M - k] = cscale(0.5f, cadd_mi(S, O));   // E - i O = (E.x + O.y, E.y - O.x)
+        };
+        if (F::kStatic) {
+#pragma unroll
+            for (int i = 0; i < UIT; ++i) {
+                const int k = lane + 32 * i;
+                if (2 * k <= M) tangle(k, p_mul(tw[k], make_float2(1.f, -1.f)));   // contiguous table read, conflict-free
+            }
+        } else {
+            for (int k = lane; 2 * k <= M; k += 32) tangle(k, p_mul(tw[k], make_float2(1.f, -1.f)));
         }
         __syncwarp();
-        const float2* res = F::run(A, B, tw, a.plan, 2, lane);
+        const float2* res = F::run(A, B, tw, twr, a.plan, 2, lane);
         float2* row = a.spec + (size_t)line * pitch;
         for (int n = lane; n < M; n += 32) {
             const float2 r = res[n];
@@ -545,7 +582,8 @@ __global__ void __launch_bounds__(PCM_THREADS) k_fft_x_c2r_w(const __grid_consta
     }
 }
 
-typedef FftWStatic<270, 2, 9, 6, 5> FftW270;
+typedef FftWStatic<270, 2, 9, 6, 5> FftW270;     // register twiddles (c2r: 3 CTAs / SM)
+typedef FftWStaticS<270, 2, 9, 6, 5> FftW270S;   // shared-memory stage tables (r2c: 4 CTAs / SM)
 
 // ------------------------------------------------------------------------------------------
 // strided passes (y and z)
@@ -981,7 +1019,7 @@ struct PearsonArgs {
 // Row-chunk-major traversal: a warp owns PR_ROWS consecutive rows of image 1 and evaluates EVERY
 // candidate on them before moving on, so all candidates stream through the volumes in lockstep and
 // the second..K-th read of a row is an L1/L2 hit (DRAM traffic ~ one sweep instead of K sweeps).
-#define PR_ROWS 8
+#define PR_ROWS 16
 #define PR_MLP 8
 
 __device__ __forceinline__ void pr_acc(unsigned int va, unsigned int vb, unsigned int& ra, unsigned int& rb,
@@ -1002,6 +1040,7 @@ __device__ __forceinline__ void pearson_u16(const PearsonArgs& a, int ncand, uns
     const bool even_rows = !(a.dx & 1) && !((size_t)i1 & 3) && !((size_t)i2 & 3);
     for (long long ch = (long long)blockIdx.x * nw + wid; ch < nchunks; ch += (long long)gridDim.x * nw) {
         const long long r0 = ch * PR_ROWS;
+        const int z0 = (int)(r0 / a.dy), y0 = (int)(r0 - (long long)z0 * a.dy);
         for (int c = 0; c < ncand; ++c) {
             const PearsonCand cd = a.cands[c];
             unsigned long long sa = 0, sb = 0, saa = 0, sbb = 0, sab = 0;
@@ -1011,7 +1050,8 @@ __device__ __forceinline__ void pearson_u16(const PearsonArgs& a, int ncand, uns
             for (int rr = 0; rr < PR_ROWS; ++rr) {
                 const long long r = r0 + rr;
                 if (r >= nrows) break;
-                const int z = (int)(r / a.dy), y = (int)(r - (long long)z * a.dy);
+                int z = z0, y = y0 + rr;          // (z, y) of row r0 + rr without a 64-bit division per row
+                while (y >= a.dy) { y -= a.dy; ++z; }
                 const int yy = y - cd.o1[1], zz = z - cd.o1[2];
                 if (yy < 0 || yy >= cd.sz[1] || zz < 0 || zz >= cd.sz[2]) continue;
                 any = true;
@@ -1516,7 +1556,7 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c<FftX270>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c<FftX270L8>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c_tma<FftX270L8>, 0))) return rc;
-        if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c_w<FftW270>, 0))) return rc;
+        if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c_w<FftW270S>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_r2c_w<FftWGeneric>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r_w<FftW270>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r_w<FftWGeneric>, 0))) return rc;
@@ -1572,7 +1612,7 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
             t.n_lines = 2LL * g.P[2] * g.P[1];
             const int per_sm = std::max(1, std::min(6, (int)(PCM_SMEM_MAX / (smem_w + 1024))));
             const int nctas = (int)std::min<long long>((t.n_lines + 7) / 8, (long long)ctx->sm_count * per_sm);
-            if (g.M == FftW270::N && env_int("BS_FFT_STATIC", 1)) k_fft_x_r2c_w<FftW270><<<nctas, PCM_THREADS, smem_w, ctx->stream>>>(t);
+            if (g.M == FftW270S::N && env_int("BS_FFT_STATIC", 1)) k_fft_x_r2c_w<FftW270S><<<nctas, PCM_THREADS, smem_w, ctx->stream>>>(t);
             else k_fft_x_r2c_w<FftWGeneric><<<nctas, PCM_THREADS, smem_w, ctx->stream>>>(t);
         } else if (tma_ok) {
             XR2CTmaArgs t;

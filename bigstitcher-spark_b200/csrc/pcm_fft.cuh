@@ -406,11 +406,87 @@ __device__ __forceinline__ float2* fft_line_wg(float2* a, float2* b, const float
     return a;
 }
 
-template <int N, int R, int LS, int TWMUL>
-__device__ __forceinline__ void fft_stage_ws(const float2* __restrict__ in, float2* __restrict__ out,
-                                             const float2* __restrict__ tw, int lane) {
+// Per-lane twiddles of the static warp-private plan, kept in REGISTERS for the whole kernel: a lane's items of a
+// stage are j = lane + 32 it, so its twiddles W^(q (j % LS) step) never change from line to line.  The x passes are
+// shared-memory-bandwidth bound (ncu: 70-87 % of the LSU wavefront peak, a third of it bank conflicts from the
+// stride-(q k step) table reads); this removes every twiddle LDS from the steady state.
+template <int N, int R, int LS>
+struct WStageTw {
+    static constexpr int m = N / R;
+    static constexpr int iters = (m + 31) / 32;
+    float2 w[LS > 1 ? iters : 1][LS > 1 ? R - 1 : 1];
+    __device__ __forceinline__ float2 get(int it, int q, int) const { return w[it][q - 1]; }
+    template <int TWMUL>
+    __device__ __forceinline__ void init(const float2* __restrict__ tw, int lane) {
+        if constexpr (LS > 1) {
+            constexpr int twstep = (N / (LS * R)) * TWMUL;
+#pragma unroll
+            for (int it = 0; it < iters; ++it) {
+                const int j = min(lane + 32 * it, m - 1);
+                const int ts = (j % LS) * twstep;
+#pragma unroll
+                for (int q = 1; q < R; ++q) w[it][q - 1] = tw[q * ts];
+            }
+        }
+    }
+};
+
+template <int N, int LS, int TWMUL, int R, int... Rest>
+struct WLineTw {
+    WStageTw<N, R, LS> head;
+    WLineTw<N, LS * R, TWMUL, Rest...> tail;
+    __device__ __forceinline__ void init(const float2* __restrict__ tw, int lane) {
+        head.template init<TWMUL>(tw, lane);
+        tail.init(tw, lane);
+    }
+};
+template <int N, int LS, int TWMUL, int R>
+struct WLineTw<N, LS, TWMUL, R> {
+    WStageTw<N, R, LS> head;
+    __device__ __forceinline__ void init(const float2* __restrict__ tw, int lane) { head.template init<TWMUL>(tw, lane); }
+};
+
+// The alternative for kernels that cannot spare the registers (the r2c pass needs 4 CTAs per SM to hide its row
+// loads): compact per-stage tables in shared memory, tab[(q - 1) * LS + k] -- consecutive lanes (consecutive k)
+// read consecutive entries, so the reads are conflict-free (the stride-(q k step) reads of the full table were not).
+template <int N, int R, int LS, int OFF>
+struct WStageTwS {
+    const float2* tab;
+    __device__ __forceinline__ float2 get(int, int q, int k) const { return tab[OFF + (q - 1) * LS + k]; }
+};
+template <int N, int LS, int TWMUL, int OFF, int R, int... Rest>
+struct WLineTwS {
+    static constexpr int cnt = LS > 1 ? (R - 1) * LS : 0;
+    WStageTwS<N, R, LS, OFF> head;
+    WLineTwS<N, LS * R, TWMUL, OFF + cnt, Rest...> tail;
+    static constexpr int total = cnt + WLineTwS<N, LS * R, TWMUL, OFF + cnt, Rest...>::total;
+    __device__ __forceinline__ void init(const float2* tab, int) { head.tab = tab; tail.init(tab, 0); }
+    // block-cooperative: fill dst[OFF ...] from the full table twg[i] = e^{-2 pi i i / (N TWMUL)}
+    static __device__ __forceinline__ void build(float2* dst, const float2* __restrict__ twg, int tid, int nt) {
+        if constexpr (LS > 1) {
+            constexpr int twstep = (N / (LS * R)) * TWMUL;
+            for (int i = tid; i < cnt; i += nt) dst[OFF + i] = twg[(i / LS + 1) * (i % LS) * twstep];
+        }
+        WLineTwS<N, LS * R, TWMUL, OFF + cnt, Rest...>::build(dst, twg, tid, nt);
+    }
+};
+template <int N, int LS, int TWMUL, int OFF, int R>
+struct WLineTwS<N, LS, TWMUL, OFF, R> {
+    static constexpr int cnt = LS > 1 ? (R - 1) * LS : 0;
+    static constexpr int total = cnt;
+    WStageTwS<N, R, LS, OFF> head;
+    __device__ __forceinline__ void init(const float2* tab, int) { head.tab = tab; }
+    static __device__ __forceinline__ void build(float2* dst, const float2* __restrict__ twg, int tid, int nt) {
+        if constexpr (LS > 1) {
+            constexpr int twstep = (N / (LS * R)) * TWMUL;
+            for (int i = tid; i < cnt; i += nt) dst[OFF + i] = twg[(i / LS + 1) * (i % LS) * twstep];
+        }
+    }
+};
+
+template <int N, int R, int LS, class ST>
+__device__ __forceinline__ void fft_stage_ws(const float2* __restrict__ in, float2* __restrict__ out, const ST& st, int lane) {
     constexpr int m = N / R;
-    constexpr int twstep = (N / (LS * R)) * TWMUL;
     constexpr int iters = (m + 31) / 32;
 #pragma unroll
     for (int it = 0; it < iters; ++it) {
@@ -421,9 +497,8 @@ __device__ __forceinline__ void fft_stage_ws(const float2* __restrict__ in, floa
 #pragma unroll
         for (int q = 0; q < R; ++q) x[q] = in[j + q * m];
         if (LS > 1) {
-            const int ts = k * twstep;
 #pragma unroll
-            for (int q = 1; q < R; ++q) x[q] = cmulf(x[q], tw[q * ts]);
+            for (int q = 1; q < R; ++q) x[q] = cmulf(x[q], st.get(it, q, k));
         }
         dft<R>(x);
         float2* o = out + (j - k) * R + k;
@@ -433,17 +508,24 @@ __device__ __forceinline__ void fft_stage_ws(const float2* __restrict__ in, floa
     __syncwarp();
 }
 
-template <int N, int LS, int TWMUL, int R, int... Rest>
-__device__ __forceinline__ float2* fft_line_ws(float2* a, float2* b, const float2* tw, int lane) {
-    fft_stage_ws<N, R, LS, TWMUL>(a, b, tw, lane);
+template <int N, int LS, int TWMUL, int R, int... Rest, class LT>
+__device__ __forceinline__ float2* fft_line_ws(float2* a, float2* b, const LT& tw, int lane) {
+    fft_stage_ws<N, R, LS>(a, b, tw.head, lane);
     if constexpr (sizeof...(Rest) == 0) return b;
-    else return fft_line_ws<N, LS * R, TWMUL, Rest...>(b, a, tw, lane);
+    else return fft_line_ws<N, LS * R, TWMUL, Rest...>(b, a, tw.tail, lane);
 }
+
+struct WNoTw {
+    static constexpr int total = 0;
+    __device__ __forceinline__ void init(const float2*, int) {}
+};
 
 struct FftWGeneric {
     static constexpr bool kStatic = false;
+    static constexpr bool kSmemTw = false;
     static constexpr int N = 0;
-    static __device__ __forceinline__ float2* run(float2* a, float2* b, const float2* tw, const FftPlan& plan,
+    typedef WNoTw Tw;            // twiddles stay in the shared table
+    static __device__ __forceinline__ float2* run(float2* a, float2* b, const float2* tw, const Tw&, const FftPlan& plan,
                                                   int twmul, int lane) {
         return fft_line_wg(a, b, tw, plan, twmul, lane);
     }
@@ -452,8 +534,24 @@ struct FftWGeneric {
 template <int N_, int TWMUL_, int... Rs>
 struct FftWStatic {
     static constexpr bool kStatic = true;
+    static constexpr bool kSmemTw = false;
     static constexpr int N = N_;
-    static __device__ __forceinline__ float2* run(float2* a, float2* b, const float2* tw, const FftPlan&, int, int lane) {
-        return fft_line_ws<N_, 1, TWMUL_, Rs...>(a, b, tw, lane);
+    typedef WLineTw<N_, 1, TWMUL_, Rs...> Tw;   // per-lane register twiddles, Tw::init once per kernel
+    static __device__ __forceinline__ float2* run(float2* a, float2* b, const float2*, const Tw& twr, const FftPlan&, int,
+                                                  int lane) {
+        return fft_line_ws<N_, 1, TWMUL_, Rs...>(a, b, twr, lane);
+    }
+};
+
+// same plan, twiddles in compact conflict-free shared-memory tables (Tw::build once per CTA, Tw::total entries)
+template <int N_, int TWMUL_, int... Rs>
+struct FftWStaticS {
+    static constexpr bool kStatic = true;
+    static constexpr bool kSmemTw = true;
+    static constexpr int N = N_;
+    typedef WLineTwS<N_, 1, TWMUL_, 0, Rs...> Tw;
+    static __device__ __forceinline__ float2* run(float2* a, float2* b, const float2*, const Tw& twr, const FftPlan&, int,
+                                                  int lane) {
+        return fft_line_ws<N_, 1, TWMUL_, Rs...>(a, b, twr, lane);
     }
 };

@@ -105,7 +105,7 @@ SYMBOLS = [
     "bs_pcm_default_params", "bs_pcm_pair", "bs_pcm_batch", "bs_pcm_volumes_batch", "bs_good_fft_size", "bs_pcm_debug_pcm",
     "bs_fuse_default_params", "bs_volume_upload", "bs_volume_upload_async", "bs_volume_wrap", "bs_volume_free",
     "bs_content_weights", "bs_volume_info", "bs_volume_download", "bs_volume_devptr", "bs_downsample", "bs_fuse_block", "bs_fuse_blocks",
-    "bs_fuse_block_to_volume", "bs_fuse_accumulate", "bs_fuse_finish", "bs_dog_default_params", "bs_dog_detect",
+    "bs_fuse_block_to_volume", "bs_fuse_accumulate", "bs_fuse_finish", "bs_mask_blocks", "bs_dog_default_params", "bs_dog_detect",
     "bs_comm_unique_id", "bs_comm_init", "bs_comm_destroy", "bs_fuse_allreduce",
 ]
 
@@ -156,6 +156,7 @@ def load_library():
     lib.bs_downsample.argtypes = [vp, ull, P(ip), P(ull)]
     lib.bs_fuse_block.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), vp, ip]
     lib.bs_fuse_blocks.argtypes = [vp, P(ViewC), ip, ip, P(ll), P(ll), P(FuseParamsC), P(vp), ip]
+    lib.bs_mask_blocks.argtypes = [vp, P(ViewC), ip, ip, P(ll), P(ll), P(C.c_double), ip, ip, P(vp), ip]
     lib.bs_fuse_block_to_volume.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), P(ull)]
     lib.bs_fuse_accumulate.argtypes = [vp, P(ViewC), ip, P(ll), P(ll), P(FuseParamsC), vp, vp]
     lib.bs_fuse_finish.argtypes = [vp, vp, vp, ll, P(FuseParamsC), vp, ip]
@@ -480,6 +481,26 @@ class Context:
             ptrs[i] = p
             keep.append(k)
         self._check(self.lib.bs_fuse_blocks(self.h, arr, n, nb, bmin, bsz, C.byref(params), ptrs, 1 if on_dev else 0))
+        return outs
+
+    def mask_blocks(self, views, block_mins_xyz, block_sizes_xyz, mask_offset=(0.0, 0.0, 0.0), out_dtype=DTYPE_U8,
+                    out_big_endian=False):
+        """`--masks` mode for a list of blocks: arrays [z,y,x] that are 255 / 65535 / 1.0 where any view covers the
+        voxel (views need src_to_world and full_dims or a resident volume; no image data is read)."""
+        arr, n = views if isinstance(views, tuple) else self.make_views(views)
+        nb = len(block_mins_xyz)
+        bmin = (C.c_longlong * (3 * max(nb, 1)))()
+        bsz = (C.c_longlong * (3 * max(nb, 1)))()
+        for i in range(nb):
+            bmin[3 * i:3 * i + 3] = [int(v) for v in block_mins_xyz[i]]
+            bsz[3 * i:3 * i + 3] = [int(v) for v in block_sizes_xyz[i]]
+        dt = np.dtype(_BS2NP[out_dtype])
+        if out_big_endian and dt.itemsize > 1:
+            dt = dt.newbyteorder(">")
+        outs = [np.empty(tuple(int(v) for v in s)[::-1], dtype=dt) for s in block_sizes_xyz]
+        ptrs = (C.c_void_p * max(nb, 1))(*[o.ctypes.data for o in outs])
+        off = (C.c_double * 3)(*[float(v) for v in mask_offset])
+        self._check(self.lib.bs_mask_blocks(self.h, arr, n, nb, bmin, bsz, off, int(out_dtype), 1 if out_big_endian else 0, ptrs, 0))
         return outs
 
     def fuse_block_to_volume(self, views, block_min_xyz, block_size_xyz, params: FuseParamsC | None = None) -> int:

@@ -216,6 +216,15 @@ int bs_fuse_block_to_volume(bs_ctx* ctx, const bs_view* views, int n_views, cons
                             const long long block_size[3], const bs_fuse_params* params,
                             unsigned long long* out_handle);
 
+/* `affine-fusion --masks [--maskOffset x,y,z]` (J/fusion/GenerateComputeBlockMasks.java:84-176, called at
+ * J/SparkAffineFusion.java:564-578): instead of fusing, every block voxel becomes "on" (255 / 65535 / 1.0f for
+ * U8 / U16 / F32) when its back-projection into ANY view lies inside [0 - mask_offset, dim - 1 + mask_offset]
+ * (source pixels, all three axes).  Only view geometry is used: src_to_world and full_dims (or, when full_dims is 0,
+ * the dims of vol_handle).  Same block-list form and output conventions as bs_fuse_blocks. */
+int bs_mask_blocks(bs_ctx* ctx, const bs_view* views, int n_views, int n_blocks, const long long* block_min,
+                   const long long* block_size, const double mask_offset[3], int out_dtype, int out_big_endian,
+                   void* const* outs, int out_on_device);
+
 /* view-sharded mode: accumulate this context's views into partial sums
  * sum_wi / sum_w (device float32, block_size elements each, NOT cleared), to be all-reduced
  * across devices by the caller (NCCL) and finished with bs_fuse_finish. */

@@ -81,11 +81,11 @@ std::vector<bs_view> unpack_views(JNIEnv* env, jint n, jdoubleArray models, jlon
     std::vector<bs_view> v((size_t)n);
     if (n == 0) return v;
     std::vector<jdouble> m((size_t)n * 12);
-    std::vector<jlong> h((size_t)n * 2), w((size_t)n * 6, 0);
-    std::vector<jfloat> b((size_t)n * 6);
+    std::vector<jlong> h((size_t)n * 2, 0), w((size_t)n * 6, 0);
+    std::vector<jfloat> b((size_t)n * 6, 0.f);
     env->GetDoubleArrayRegion(models, 0, n * 12, m.data());
-    env->GetLongArrayRegion(handles, 0, n * 2, h.data());
-    env->GetFloatArrayRegion(blend, 0, n * 6, b.data());
+    if (handles) env->GetLongArrayRegion(handles, 0, n * 2, h.data());
+    if (blend) env->GetFloatArrayRegion(blend, 0, n * 6, b.data());
     if (windows) env->GetLongArrayRegion(windows, 0, n * 6, w.data());
     for (jint i = 0; i < n; ++i) {
         memset(&v[i], 0, sizeof(bs_view));
@@ -350,6 +350,23 @@ JF(void, fuseBlocks)(JNIEnv* env, jclass, jlong ctx, jint nViews, jdoubleArray m
     for (jsize i = 0; i < n; ++i) outs[(size_t)i] = env->GetDirectBufferAddress(env->GetObjectArrayElement(dests, i));
     const bs_fuse_params p = fuse_params(env, iparams, dparams);
     failed(env, ctx, bs_fuse_blocks(C(ctx), v.data(), nViews, n, mn.data(), sz.data(), &p, outs.data(), 0));
+}
+
+// --masks mode: views carry geometry only (models + windows{fullDims, 0}); maskOffset {x, y, z} in source pixels
+JF(void, maskBlocks)(JNIEnv* env, jclass, jlong ctx, jint nViews, jdoubleArray models, jlongArray handles, jlongArray windows,
+                     jlongArray blockMins, jlongArray blockSizes, jdoubleArray maskOffset, jint outDtype, jint outBigEndian,
+                     jobjectArray dests) {
+    std::vector<bs_view> v = unpack_views(env, nViews, models, handles, nullptr, windows);
+    const jsize n = env->GetArrayLength(dests);
+    std::vector<jlong> mnj((size_t)n * 3), szj((size_t)n * 3);
+    env->GetLongArrayRegion(blockMins, 0, n * 3, mnj.data());
+    env->GetLongArrayRegion(blockSizes, 0, n * 3, szj.data());
+    std::vector<long long> mn(mnj.begin(), mnj.end()), sz(szj.begin(), szj.end());
+    std::vector<void*> outs((size_t)n);
+    for (jsize i = 0; i < n; ++i) outs[(size_t)i] = env->GetDirectBufferAddress(env->GetObjectArrayElement(dests, i));
+    jdouble off[3];
+    env->GetDoubleArrayRegion(maskOffset, 0, 3, off);
+    failed(env, ctx, bs_mask_blocks(C(ctx), v.data(), nViews, n, mn.data(), sz.data(), off, outDtype, outBigEndian, outs.data(), 0));
 }
 
 JF(jlong, fuseBlockToVolume)(JNIEnv* env, jclass, jlong ctx, jint nViews, jdoubleArray models, jlongArray handles, jfloatArray blend,

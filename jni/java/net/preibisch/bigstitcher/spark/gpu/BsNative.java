@@ -60,6 +60,9 @@ public final class BsNative
 			long[] blockMin, long[] blockSize, int[] iparams, double[] dparams, Object dest );
 	public static native void fuseBlocks( long ctx, int nViews, double[] models, long[] handles, float[] blend, long[] windows,
 			long[] blockMins, long[] blockSizes, int[] iparams, double[] dparams, Object[] dests );
+	/** --masks: 255 / 65535 / 1.0f where any view's (grown) pixel grid covers the voxel (GenerateComputeBlockMasks) */
+	public static native void maskBlocks( long ctx, int nViews, double[] models, long[] handles, long[] windows,
+			long[] blockMins, long[] blockSizes, double[] maskOffset, int outDtype, int outBigEndian, Object[] dests );
 	public static native long fuseBlockToVolume( long ctx, int nViews, double[] models, long[] handles, float[] blend, long[] windows,
 			long[] blockMin, long[] blockSize, int[] iparams, double[] dparams );
 	public static native void fuseAccumulate( long ctx, int nViews, double[] models, long[] handles, float[] blend,

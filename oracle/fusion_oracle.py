@@ -325,3 +325,24 @@ def downsample2x(vol, factors_xyz):
         else:
             out = ((a.astype(np.uint32) + b.astype(np.uint32) + 1) >> 1).astype(vol.dtype)
     return out
+
+
+def mask_block(views_geom, block_min_xyz, block_size_xyz, mask_offset=(0.0, 0.0, 0.0), dtype="uint8"):
+    """`--masks` mode (src/main/java/net/preibisch/bigstitcher/spark/fusion/GenerateComputeBlockMasks.java:119-176):
+    a voxel is on when its back-projection l = M^-1 (world) satisfies min_d <= l_d <= max_d for EVERY axis of ANY view,
+    min = 0 - offset, max = dim - 1 + offset (:127-128, :141-147); on = 255 / 65535 / 1.0f (:154-176).
+    ``views_geom``: [(src_to_world 3x4, dims_xyz)]."""
+    bx, by, bz = (int(v) for v in block_size_xyz)
+    z, y, x = np.meshgrid(np.arange(bz, dtype=np.float64) + block_min_xyz[2], np.arange(by, dtype=np.float64) + block_min_xyz[1],
+                          np.arange(bx, dtype=np.float64) + block_min_xyz[0], indexing="ij")
+    on = np.zeros((bz, by, bx), dtype=bool)
+    off = np.asarray(mask_offset, dtype=np.float64)
+    for M, dims in views_geom:
+        inv = np.linalg.inv(np.vstack([np.asarray(M, dtype=np.float64).reshape(3, 4), [0, 0, 0, 1]]))
+        inside = np.ones_like(on)
+        for d in range(3):
+            l = inv[d, 0] * x + inv[d, 1] * y + inv[d, 2] * z + inv[d, 3]
+            inside &= ~((l < 0.0 - off[d]) | (l > (dims[d] - 1) + off[d]))
+        on |= inside
+    top = {"uint8": 255, "uint16": 65535, "float32": 1.0}[dtype]
+    return np.where(on, top, 0).astype(dtype)

@@ -114,5 +114,14 @@ class FakeContext:
             return outs
         return res
 
+    def mask_blocks(self, views, block_mins, block_sizes, mask_offset=(0.0, 0.0, 0.0), out_dtype=2, out_big_endian=False):
+        geom = []
+        for v in views:
+            fd = tuple(int(x) for x in v.get("full_dims", (0, 0, 0)))
+            if fd[0] <= 0:
+                fd = tuple(self.vols[v["vol_handle"]].shape[::-1])
+            geom.append((np.asarray(v["src_to_world"], dtype=np.float64).reshape(3, 4), fd))
+        return [fo.mask_block(geom, mn, sz, mask_offset, _DT[out_dtype]) for mn, sz in zip(block_mins, block_sizes)]
+
     def fuse_block_to_volume(self, views, block_min, block_size, params=None):
         return self.volume_upload(self.fuse_block(views, block_min, block_size, params))

@@ -83,6 +83,18 @@ def test_fusion_commands_n5_zarr_and_multires(tmp_path):
     assert dz == ["0"] and mz["dtype"] == "uint16"
     assert np.array_equal(stz.read_volume("0"), fo.convert_output(want, "uint16", 0.0, 4000.0))
 
+    # storage blocks that are whole kernel tiles (64 x 16 x 8) leave the device as finished chunks: big-endian N5
+    # payloads, little-endian zarr chunks, no host re-striding
+    for name, dtype in (("packed.n5", "float32"), ("packed.zarr", "uint16")):
+        outp = str(tmp_path / name)
+        commands.create_fusion_container(xml, outp, block_size=(64, 16, 8), dtype=dtype, min_intensity=0.0, max_intensity=4000.0)
+        dp = commands.affine_fusion(outp, ctx, "AVG_BLEND", block_scale=(1, 2, 3))
+        if name.endswith(".n5"):
+            got = bn5.read_fusion_container(outp)[0].read_volume(dp[0])
+        else:
+            got = bz.read_fusion_container_zarr(outp)[0].read_volume(dp[0])
+        assert np.array_equal(got, want if dtype == "float32" else fo.convert_output(want, "uint16", 0.0, 4000.0))
+
     # multi-resolution OME-ZARR (the reference's default container + --multiRes / -ds), with a pyramid step the
     # super-blocks are NOT multiples of: levels are rebuilt from the container's level l-1 (the reference's way)
     outm = str(tmp_path / "fused_mr.zarr")
@@ -184,3 +196,21 @@ def test_fuse_volume_retries_failed_blocks(tmp_path):
     Flaky.fails = 10 ** 6
     with pytest.raises(RuntimeError):
         fusion.fuse_volume(sup, (16, 16, 16), (8, 8, 8), (1, 1, 1), retries=2)
+
+
+def test_masks_mode_writes_coverage_and_its_pyramid(tmp_path):
+    """`affine-fusion --masks [--maskOffset]`: geometry only, 255 where a view covers the voxel, pyramid from that s0."""
+    xml, vols, tiles, planted, nominal = _dataset(tmp_path)
+    ctx = FakeContext()
+    out = str(tmp_path / "masks.n5")
+    commands.create_fusion_container(xml, out, block_size=(16, 16, 16), dtype="uint8", min_intensity=0.0, max_intensity=255.0,
+                                     downsamplings=[(2, 2, 1)])
+    ds = commands.affine_fusion(out, ctx, "AVG_BLEND", block_scale=(2, 2, 1), masks=True, mask_offset=(-1.0, 0.0, 0.0))
+    st, meta = bn5.read_fusion_container(out)
+    ext = (nominal + 48, nominal + 48, 48)
+    geom = [(synth.translation(t["translation_xyz"]), vols[t["setup"]].shape[::-1]) for t in tiles]
+    want = fo.mask_block(geom, (0, 0, 0), ext, (-1.0, 0.0, 0.0), "uint8")
+    got = st.read_volume(ds[0])
+    assert np.array_equal(got, want) and 0 < np.count_nonzero(want) < want.size
+    assert np.array_equal(st.read_volume("ch0tp0/s1"), fo.downsample2x(want, (2, 2, 1)))
+    assert ctx.calls["fuse"] == 0 and not ctx.vols          # nothing was fused, no image data touched

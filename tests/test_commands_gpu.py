@@ -45,6 +45,14 @@ def test_stitching_then_fusion_end_to_end(ctx, tmp_path):
     err = np.abs(fused - want) / np.maximum(np.abs(want), 1.0)
     assert (err > 1e-4).mean() < 1e-3 and fused.shape == want.shape
 
+    # storage blocks that are whole kernel tiles are packed (and, for N5, byte-swapped) on the device: same volume up to
+    # the rounding of tile-relative coordinates (tiles are anchored at the block origin)
+    outc = str(tmp_path / "fused_cells.n5")
+    commands.create_fusion_container(xml, outc, block_size=(64, 32, 16))
+    dc = commands.affine_fusion(outc, ctx, "AVG_BLEND", block_scale=(1, 2, 3))
+    packed = bn5.read_fusion_container(outc)[0].read_volume(dc[0])
+    assert np.allclose(packed, fused, rtol=2e-6, atol=1e-3)
+
     # --multiRes: pyramid levels derived on the device from the resident fused block
     outm = str(tmp_path / "fused_mr.n5")
     commands.create_fusion_container(xml, outm, block_size=(32, 32, 32), downsamplings=[(2, 2, 1), (2, 2, 2)])

@@ -442,3 +442,34 @@ def test_big_endian_output_is_the_byte_swapped_block(ctx, out_dtype, ft, rot):
         assert a.tobytes() == b.byteswap().tobytes()
     for h in handles:
         ctx.volume_free(h)
+
+
+@pytest.mark.parametrize("out_dtype", ["uint8", "uint16", "float32"])
+def test_masks_mode_matches_oracle(ctx, out_dtype):
+    """bs_mask_blocks (--masks): bit-identical to the oracle, geometry only (no volumes), rotated and scaled views,
+    mask offset, big-endian payloads, more views than one kernel-parameter group."""
+    dt = {"float32": bsgpu.native.DTYPE_F32, "uint16": bsgpu.native.DTYPE_U16, "uint8": bsgpu.native.DTYPE_U8}[out_dtype]
+    geom = [(synth.translation((2.0, 0.0, 0.0)), (40, 30, 20)),
+            (np.vstack([synth.rot_z(7.0, center_xyz=(20, 15, 0)), [0, 0, 0, 1]]) @ np.vstack([synth.translation((35.25, 4.5, 3.0)), [0, 0, 0, 1]]), (40, 30, 20)),
+            (np.diag([1.0, 1.0, 2.5, 1.0]) @ np.vstack([synth.translation((10.0, 28.0, 1.0)), [0, 0, 0, 1]]), (30, 20, 8))]
+    geom = [(np.asarray(M)[:3], d) for M, d in geom]
+    views = [dict(src_to_world=M, vol_handle=0, full_dims=d) for M, d in geom]
+    mins, sizes = [(-3, -2, -1), (30, 10, 5)], [(90, 60, 30), (33, 17, 9)]
+    for off in ((0.0, 0.0, 0.0), (1.5, 0.0, -0.5)):
+        got = ctx.mask_blocks(views, mins, sizes, off, dt)
+        be = ctx.mask_blocks(views, mins, sizes, off, dt, out_big_endian=True)
+        for mn, sz, g, b in zip(mins, sizes, got, be):
+            want = fo.mask_block(geom, mn, sz, off, out_dtype)
+            assert np.array_equal(g, want) and 0 < np.count_nonzero(want) < want.size
+            assert np.array_equal(b.astype(g.dtype), g)
+    many = [dict(src_to_world=synth.translation((3.0 * i, 0.0, 0.0)), vol_handle=0, full_dims=(2, 4, 4)) for i in range(70)]
+    g = ctx.mask_blocks(many, [(0, 0, 0)], [(220, 4, 4)], (0, 0, 0), dt)[0]
+    want = fo.mask_block([(v["src_to_world"], v["full_dims"]) for v in many], (0, 0, 0), (220, 4, 4), (0, 0, 0), out_dtype)
+    assert np.array_equal(g, want) and g[0, 0, 208] > 0 and g[0, 0, 209] == 0
+    # dims from a resident volume when full_dims is not given
+    h = ctx.volume_upload(np.zeros((6, 10, 20), np.uint16))
+    g = ctx.mask_blocks([dict(src_to_world=synth.translation((2.0, 0.0, 0.0)), vol_handle=h)], [(0, 0, 0)], [(30, 12, 8)], (0, 0, 0), dt)[0]
+    assert np.array_equal(g, fo.mask_block([(synth.translation((2.0, 0.0, 0.0)), (20, 10, 6))], (0, 0, 0), (30, 12, 8), (0, 0, 0), out_dtype))
+    ctx.volume_free(h)
+    with pytest.raises(bsgpu.BsError):
+        ctx.mask_blocks([dict(src_to_world=synth.translation((0, 0, 0)), vol_handle=0)], [(0, 0, 0)], [(4, 4, 4)])

@@ -154,3 +154,21 @@ def test_c_restatement_matches_numpy_oracle():
         assert np.allclose(got, want, rtol=2e-6, atol=1e-4)
         assert np.array_equal(got == 0, want == 0)
     assert c_fusion.num_threads() >= 1
+
+
+def test_mask_block_semantics():
+    """--masks: closed interval [0 - off, dim - 1 + off] on every axis of any view; 255 / 65535 / 1.0."""
+    M0 = synth.translation((2.0, 0.0, 0.0))
+    M1 = synth.translation((30.5, 3.0, 1.0))
+    geom = [(M0, (20, 10, 6)), (M1, (10, 10, 6))]
+    m = fo.mask_block(geom, (0, 0, 0), (48, 16, 8), (0.0, 0.0, 0.0), "uint8")
+    assert m.dtype == np.uint8 and set(np.unique(m)) == {0, 255}
+    assert m[0, 0, 2] == 255 and m[0, 0, 1] == 0 and m[0, 0, 21] == 255 and m[0, 0, 22] == 0      # view 0: x in [2, 21]
+    assert m[1, 3, 31] == 255 and m[1, 3, 30] == 0 and m[1, 3, 39] == 255 and m[1, 3, 40] == 0     # view 1: x in [30.5, 39.5]
+    assert m[0, 3, 31] == 0 and m[7, 3, 31] == 0                                                   # z in [1, 6]
+    g = fo.mask_block(geom, (0, 0, 0), (48, 16, 8), (1.0, 0.0, 0.5), "uint16")
+    assert g.dtype == np.uint16 and g[0, 0, 1] == 65535 and g[0, 0, 0] == 0 and g[0, 0, 22] == 65535
+    assert g[0, 3, 31] == 0 and g[1, 3, 30] == 65535                                               # z grows by 0.5 only
+    f = fo.mask_block(geom, (0, 0, 0), (48, 16, 8), (0.0, 0.0, 0.0), "float32")
+    assert f.dtype == np.float32 and np.array_equal(f > 0, m > 0) and f.max() == 1.0
+    assert not fo.mask_block([], (0, 0, 0), (4, 4, 4)).any()
