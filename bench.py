@@ -146,6 +146,19 @@ def cpu_pcm_sample(n, procs, threads, repeats=1, pairs=None):
         if _CPU.get("key") != key:
             _CPU["pairs"] = [synth.shifted_pair((n, n, n), (7 - i, -5 + i, 3), seed=99 + i, margin=12, sigma=2.0) for i in range(pairs)]
             _CPU["key"] = key
+            # thread count: every logical CPU or one per physical core, whichever runs a pair faster on this box (the
+            # FFT passes are memory-bound, so SMT siblings usually lose) -- calibrated once on the first pair
+            logical = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            best = None
+            for nt in sorted({logical, c_pcm.physical_cores()}, reverse=True):
+                c_pcm.set_num_threads(nt)
+                t0 = time.perf_counter()
+                c_pcm.pcm_shift(*_CPU["pairs"][0])
+                dt = time.perf_counter() - t0
+                if best is None or dt < best[0]:
+                    best = (dt, nt)
+            c_pcm.set_num_threads(best[1])
+            _CPU["threads"] = best[1]
         times = []
         for _ in range(repeats):
             t0 = time.perf_counter()
@@ -155,6 +168,7 @@ def cpu_pcm_sample(n, procs, threads, repeats=1, pairs=None):
             times.append(time.perf_counter() - t0)
         _CPU["impl"] = f"oracle/c/pcm_oracle.c, {c_pcm.num_threads()} OpenMP threads, {pairs} pairs per step one after the other"
         _CPU["cores"] = c_pcm.num_threads()
+        _CPU["pairs_per_step"] = pairs
         return pairs / min(times), times
     except Exception:
         pass
@@ -170,6 +184,7 @@ def cpu_pcm_sample(n, procs, threads, repeats=1, pairs=None):
             times.append(time.perf_counter() - t0)
     _CPU["impl"] = f"oracle/pcm_oracle.py (numpy + scipy pocketfft), {procs} concurrent pairs x {threads} FFT threads"
     _CPU["cores"] = procs * threads
+    _CPU["pairs_per_step"] = procs
     return procs / min(times), times
 
 
@@ -183,6 +198,7 @@ def cpu_fusion_sample(procs, blocks_per_proc=2, tile=160, bs=96):
     rng = np.random.default_rng(7)
     try:
         from oracle import c_fusion
+        c_fusion.set_num_threads(_CPU.get("threads") or c_fusion.physical_cores())   # the count the PCM arm calibrated
         nthreads = c_fusion.num_threads()
         t = 320
         stride = int(t * 491 / 576)
@@ -242,7 +258,7 @@ def cpu_layout():
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path is not runnable here
     (no JVM, arithmetic in un-vendored Maven artefacts -- SURVEY.md 8c), so this arm times the
-    oracle port (numpy/scipy pocketfft) on the box's host cores.  Rank 0 only."""
+    oracle port (oracle/c/pcm_oracle.c, C / OpenMP, thread count calibrated per box) on the box's host cores.  Rank 0 only."""
     if rank != 0:
         return
     ncores, procs, threads = cpu_layout()
@@ -261,7 +277,7 @@ def run_reference(args, rank):
     sample = f"{n}^3 uint16 pairs, {_CPU.get('impl', '?')}"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": nsteps, "steps_requested": args.steps, "warmup": 1, "ms_per_step": 1000.0 * procs / value,
+        "steps": nsteps, "steps_requested": args.steps, "warmup": 1, "ms_per_step": 1000.0 * _CPU.get("pairs_per_step", procs) / value,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD_PCM if n == 512 else f"phase-correlation: {n}^3 uint16 overlap crops",
                    "sampling": f"every step is a bounded sample of that workload ({_CPU.get('impl', '?')})",

@@ -115,7 +115,6 @@ struct FuseArgs2 {
     int nwork;
     int use_blend;
     int xyaff;                    // general kernel: every view is an xy-affine + z-translation (fast z-marching tiles)
-    int swap;                     // bs_fuse_params.out_big_endian: 2-/4-byte elements are stored byte-swapped
     double cmin, cscale, ctop;
 };
 
@@ -281,6 +280,11 @@ __global__ void fuse_plan2_kernel(const ViewDev* __restrict__ views, const Block
 }
 
 // ------------------------------------------------------------------------------------------ output
+// The kernels' OUT template value = output dtype | OUT_BE: big-endian output (bs_fuse_params.out_big_endian) is a
+// compile-time property of the instantiation, so the native-order kernels carry no byte-order code at all and the
+// big-endian ones pay one PRMT per store.
+#define OUT_BE 8
+#define OUT_DT(OUT) ((OUT) & 7)
 __device__ __forceinline__ unsigned int bswap32(unsigned int v) { return __byte_perm(v, 0u, 0x0123); }
 __device__ __forceinline__ unsigned int bswap16x2(unsigned int v) { return __byte_perm(v, 0u, 0x2301); }
 
@@ -291,25 +295,28 @@ __device__ __forceinline__ unsigned int conv_int(const FuseArgs2& a, float res) 
 }
 template <int OUT>
 __device__ __forceinline__ void store1(const FuseArgs2& a, void* p, float res) {
-    if (OUT == BS_DTYPE_F32) {
-        if (a.swap) __stcs((unsigned int*)p, bswap32(__float_as_uint(res)));
+    constexpr bool BE = (OUT & OUT_BE) != 0;
+    if (OUT_DT(OUT) == BS_DTYPE_F32) {
+        if (BE) __stcs((unsigned int*)p, bswap32(__float_as_uint(res)));
         else __stcs((float*)p, res);
     } else {
         const unsigned int c = conv_int<OUT>(a, res);
-        if (OUT == BS_DTYPE_U16) *(unsigned short*)p = (unsigned short)(a.swap ? bswap16x2(c) : c);
+        if (OUT_DT(OUT) == BS_DTYPE_U16) *(unsigned short*)p = (unsigned short)(BE ? bswap16x2(c) : c);
         else *(unsigned char*)p = (unsigned char)c;
     }
 }
-template <int OUT> struct OutT { using type = float; };
-template <> struct OutT<BS_DTYPE_U16> { using type = unsigned short; };
-template <> struct OutT<BS_DTYPE_U8> { using type = unsigned char; };
+template <int DT> struct OutT_ { using type = float; };
+template <> struct OutT_<BS_DTYPE_U16> { using type = unsigned short; };
+template <> struct OutT_<BS_DTYPE_U8> { using type = unsigned char; };
+template <int OUT> struct OutT { using type = typename OutT_<OUT_DT(OUT)>::type; };
 
 // store two x-adjacent voxels (x even within the tile); vec: the pair is 8-/4-/2-byte aligned and both exist
 template <int OUT>
 __device__ __forceinline__ void store_pair(const FuseArgs2& a, typename OutT<OUT>::type* p, float r0, float r1, bool has1,
                                            bool vec) {
-    if (OUT == BS_DTYPE_F32) {
-        if (a.swap) {
+    constexpr bool BE = (OUT & OUT_BE) != 0;
+    if (OUT_DT(OUT) == BS_DTYPE_F32) {
+        if (BE) {
             const unsigned int u0 = bswap32(__float_as_uint(r0)), u1 = bswap32(__float_as_uint(r1));
             if (vec && has1) __stcs((uint2*)p, make_uint2(u0, u1));
             else { __stcs((unsigned int*)p, u0); if (has1) __stcs((unsigned int*)p + 1, u1); }
@@ -319,9 +326,9 @@ __device__ __forceinline__ void store_pair(const FuseArgs2& a, typename OutT<OUT
             __stcs((float*)p, r0);
             if (has1) __stcs((float*)p + 1, r1);
         }
-    } else if (OUT == BS_DTYPE_U16) {
+    } else if (OUT_DT(OUT) == BS_DTYPE_U16) {
         unsigned int c = conv_int<OUT>(a, r0) | (conv_int<OUT>(a, r1) << 16);
-        if (a.swap) c = bswap16x2(c);
+        if (BE) c = bswap16x2(c);
         if (vec && has1) *(unsigned int*)p = c;
         else { p[0] = (unsigned short)(c & 0xffffu); if (has1) p[1] = (unsigned short)(c >> 16); }
     } else {
@@ -840,7 +847,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) fuse_tma_kernel(const __grid_cons
         // ---------------- producer warp: tile records + view items + TMA boxes, in ring order
         int it = 0, tseq = 0;
         unsigned long long fenced = 0ull;
-        const size_t esz = OUT == BS_DTYPE_F32 ? 4 : (OUT == BS_DTYPE_U16 ? 2 : 1);
+        const size_t esz = OUT_DT(OUT) == BS_DTYPE_F32 ? 4 : (OUT_DT(OUT) == BS_DTYPE_U16 ? 2 : 1);
         for (;;) {
             int w = 0;
             if (lane == 0) w = atomicAdd(a.work_ctr, 1);
@@ -1047,10 +1054,16 @@ Fuse2Ws* ws_of(bs_ctx* ctx) {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 template <bool GENERAL, bool CONTENT = false>
-void launch_kernel(int out_dtype, int grid, size_t smem, cudaStream_t s, const FuseArgs2& a) {
-    if (out_dtype == BS_DTYPE_F32) fuse_tma_kernel<GENERAL, BS_DTYPE_F32, CONTENT><<<grid, NTHREADS, smem, s>>>(a);
-    else if (out_dtype == BS_DTYPE_U16) fuse_tma_kernel<GENERAL, BS_DTYPE_U16, CONTENT><<<grid, NTHREADS, smem, s>>>(a);
-    else fuse_tma_kernel<GENERAL, BS_DTYPE_U8, CONTENT><<<grid, NTHREADS, smem, s>>>(a);
+void launch_kernel(int out_dtype, bool big_endian, int grid, size_t smem, cudaStream_t s, const FuseArgs2& a) {
+    if (out_dtype == BS_DTYPE_F32) {
+        if (big_endian) fuse_tma_kernel<GENERAL, BS_DTYPE_F32 | OUT_BE, CONTENT><<<grid, NTHREADS, smem, s>>>(a);
+        else fuse_tma_kernel<GENERAL, BS_DTYPE_F32, CONTENT><<<grid, NTHREADS, smem, s>>>(a);
+    } else if (out_dtype == BS_DTYPE_U16) {
+        if (big_endian) fuse_tma_kernel<GENERAL, BS_DTYPE_U16 | OUT_BE, CONTENT><<<grid, NTHREADS, smem, s>>>(a);
+        else fuse_tma_kernel<GENERAL, BS_DTYPE_U16, CONTENT><<<grid, NTHREADS, smem, s>>>(a);
+    } else {
+        fuse_tma_kernel<GENERAL, BS_DTYPE_U8, CONTENT><<<grid, NTHREADS, smem, s>>>(a);
+    }
 }
 
 constexpr size_t smem_bytes(bool general) {
@@ -1280,6 +1293,13 @@ int fuse2_launch(bs_ctx* ctx, const bs_view* views, int n_views, int nb, const l
         BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<true, BS_DTYPE_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg));
         BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<true, BS_DTYPE_U16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg));
         BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<true, BS_DTYPE_U8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg));
+        // big-endian instantiations (the same kernels with a byte swap in the store)
+        BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<false, BS_DTYPE_F32 | OUT_BE>, cudaFuncAttributeMaxDynamicSharedMemorySize, st));
+        BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<false, BS_DTYPE_U16 | OUT_BE>, cudaFuncAttributeMaxDynamicSharedMemorySize, st));
+        BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<false, BS_DTYPE_F32 | OUT_BE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st));
+        BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<false, BS_DTYPE_U16 | OUT_BE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, st));
+        BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<true, BS_DTYPE_F32 | OUT_BE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg));
+        BS_CUDA(ctx, cudaFuncSetAttribute(fuse_tma_kernel<true, BS_DTYPE_U16 | OUT_BE>, cudaFuncAttributeMaxDynamicSharedMemorySize, sg));
         W->attr_done = true;
     }
     FuseArgs2 a;
@@ -1290,7 +1310,6 @@ int fuse2_launch(bs_ctx* ctx, const bs_view* views, int n_views, int nb, const l
     a.hdr = (const TileHdr*)W->hdr;
     a.pool = (const ViewItem*)W->pool;
     a.use_blend = use_blend;
-    a.swap = (p->out_big_endian && bs_out_elem_size(p->out_dtype) > 1) ? 1 : 0;
     {
         const char* e = getenv("BS_FUSE_NO_XYAFF");
         a.xyaff = (xyaff && !(e && *e && *e != '0')) ? 1 : 0;
@@ -1303,9 +1322,10 @@ int fuse2_launch(bs_ctx* ctx, const bs_view* views, int n_views, int nb, const l
     {
         bs_launch_scope scope(ctx, "fuse");
         const int grid = (int)std::min<size_t>(work.size(), (size_t)ctx->sm_count);
-        if (general) launch_kernel<true>(p->out_dtype, grid, smem_bytes(true), ctx->stream, a);
-        else if (content) launch_kernel<false, true>(p->out_dtype, grid, smem_bytes(false), ctx->stream, a);
-        else launch_kernel<false>(p->out_dtype, grid, smem_bytes(false), ctx->stream, a);
+        const bool be = p->out_big_endian != 0;
+        if (general) launch_kernel<true>(p->out_dtype, be, grid, smem_bytes(true), ctx->stream, a);
+        else if (content) launch_kernel<false, true>(p->out_dtype, be, grid, smem_bytes(false), ctx->stream, a);
+        else launch_kernel<false>(p->out_dtype, be, grid, smem_bytes(false), ctx->stream, a);
     }
     BS_CUDA(ctx, cudaGetLastError());
     {

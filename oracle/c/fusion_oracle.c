@@ -46,6 +46,15 @@ static inline float voxel(const void* img, int dtype, size_t i) {
 
 static inline long long clampll(long long v, long long hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
 
+/* physical cores beat hyper-threads on these memory-bound loops: the caller picks the count */
+void fo_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int fo_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -29,6 +29,15 @@
 #define LB 16            /* lines per batch */
 #define NORM_THRESHOLD 1e-5f
 
+/* physical cores beat hyper-threads on these memory-bound loops: the caller picks the count */
+void po_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int po_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -25,6 +25,21 @@ def load():
     return _lib
 
 
+def set_num_threads(n: int):
+    load().po_set_num_threads(int(n))
+
+
+def physical_cores() -> int:
+    """Physical cores visible to this process (psutil when present, else the logical count)."""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False) or 0
+    except Exception:
+        n = 0
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    return max(1, min(n, avail)) if n else avail
+
+
 def num_threads():
     return load().po_num_threads()
 
