@@ -40,21 +40,22 @@ struct LoadArgs {
     float* out;
 };
 
-__global__ void k_dog_load(const __grid_constant__ LoadArgs a) {
-    const long long n = (long long)a.rdims[0] * a.rdims[1] * a.rdims[2];
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int x = (int)(i % a.rdims[0]);
-        const long long r = i / a.rdims[0];
-        const int y = (int)(r % a.rdims[1]), z = (int)(r / a.rdims[1]);
-        const int sx = mirror_double(a.rmin[0] + x, a.vdims[0]), sy = mirror_double(a.rmin[1] + y, a.vdims[1]);
-        const int sz = mirror_double(a.rmin[2] + z, a.vdims[2]);
-        const size_t si = ((size_t)sz * a.vdims[1] + sy) * a.vdims[0] + sx;
-        float v;
-        if (a.dtype == BS_DTYPE_U16) v = (float)__ldg((const unsigned short*)a.src + si);
-        else if (a.dtype == BS_DTYPE_F32) v = __ldg((const float*)a.src + si);
-        else v = (float)__ldg((const unsigned char*)a.src + si);
-        a.out[i] = (v - a.offset) * a.scale;
-    }
+// grid (ceil(rdims[0] / 256), rdims[1], rdims[2]): no per-voxel index division; the mirror folding only runs for
+// voxels outside the image (the halo of border blocks)
+__global__ void __launch_bounds__(256) k_dog_load(const __grid_constant__ LoadArgs a) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= a.rdims[0]) return;
+    const int y = blockIdx.y, z = blockIdx.z;
+    const long long gx = a.rmin[0] + x, gy = a.rmin[1] + y, gz = a.rmin[2] + z;
+    const int sx = (gx >= 0 && gx < a.vdims[0]) ? (int)gx : mirror_double(gx, a.vdims[0]);
+    const int sy = (gy >= 0 && gy < a.vdims[1]) ? (int)gy : mirror_double(gy, a.vdims[1]);
+    const int sz = (gz >= 0 && gz < a.vdims[2]) ? (int)gz : mirror_double(gz, a.vdims[2]);
+    const size_t si = ((size_t)sz * a.vdims[1] + sy) * a.vdims[0] + sx;
+    float v;
+    if (a.dtype == BS_DTYPE_U16) v = (float)__ldg((const unsigned short*)a.src + si);
+    else if (a.dtype == BS_DTYPE_F32) v = __ldg((const float*)a.src + si);
+    else v = (float)__ldg((const unsigned char*)a.src + si);
+    a.out[((size_t)z * a.rdims[1] + y) * a.rdims[0] + x] = (v - a.offset) * a.scale;
 }
 
 #define DOG_MAXR 64
@@ -241,19 +242,18 @@ __device__ __forceinline__ bool solve3f(const double H[3][3], const double g[3],
     return true;
 }
 
+// grid (ceil(cdims[0] / 256), cdims[1], cdims[2])
 __global__ void __launch_bounds__(256) k_dog_extrema(const __grid_constant__ ExtremaArgs a) {
-    const long long n = (long long)a.cdims[0] * a.cdims[1] * a.cdims[2];
     const long long sy = a.rdims[0], sz = (long long)a.rdims[0] * a.rdims[1];
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const int cx = (int)(i % a.cdims[0]);
-        const long long r = i / a.cdims[0];
-        const int cy = (int)(r % a.cdims[1]), cz = (int)(r / a.cdims[1]);
+    const int cx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cx < a.cdims[0]) {
+        const int cy = blockIdx.y, cz = blockIdx.z;
         const int x = a.e0[0] + cx, y = a.e0[1] + cy, z = a.e0[2] + cz;
         const float* p = a.dog + (long long)z * sz + (long long)y * sy + x;
         const float v = p[0];
         const bool cand_max = a.find_max && v >= a.thr_initial;
         const bool cand_min = a.find_min && -v >= a.thr_initial;
-        if (!cand_max && !cand_min) continue;
+        if (!cand_max && !cand_min) return;
         bool is_max = cand_max, is_min = cand_min;
         float nb[27];
 #pragma unroll
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) k_dog_extrema(const __grid_constant__ Ext
                         if (w < v) is_min = false;
                     }
                 }
-        if (!is_max && !is_min) continue;
+        if (!is_max && !is_min) return;
         double d[3] = {0.0, 0.0, 0.0};
         double val = v;
         if (a.localize) {
@@ -289,12 +289,12 @@ __global__ void __launch_bounds__(256) k_dog_extrema(const __grid_constant__ Ext
             } else {
                 d[0] = d[1] = d[2] = 0.0;
             }
-            if (fabs(val) < a.thr_final) continue;
+            if (fabs(val) < a.thr_final) return;
         } else if (fabsf(v) < a.thr_final) {
-            continue;
+            return;
         }
         const int slot = atomicAdd(a.counter, 1);
-        if (slot >= a.max_points) continue;
+        if (slot >= a.max_points) return;
         bs_dog_point& o = a.out[slot];
         o.voxel[0] = a.rmin[0] + x; o.voxel[1] = a.rmin[1] + y; o.voxel[2] = a.rmin[2] + z;
         o.loc[0] = (double)o.voxel[0] + d[0]; o.loc[1] = (double)o.voxel[1] + d[1]; o.loc[2] = (double)o.voxel[2] + d[2];
@@ -371,6 +371,8 @@ int bs_dog_detect(bs_ctx* ctx, unsigned long long vol_handle, const long long in
         rdims[d] = (int)rd;
         nreg *= rd;
     }
+    if (rdims[1] > 65535 || rdims[2] > 65535)
+        return bs_set_error(ctx, BS_ERR_ARG, "bs_dog_detect: block too large in y / z (%d x %d incl. halo, limit 65535): detect block-wise", rdims[1], rdims[2]);
     // the region's rows are padded to a multiple of 8 floats (more halo on the right: the extra columns hold real
     // mirror-extended image data, so every used voxel is unchanged) -> aligned float4 windows in the x pass
     nreg = nreg / rdims[0];
@@ -399,7 +401,7 @@ int bs_dog_detect(bs_ctx* ctx, unsigned long long vol_handle, const long long in
         a.scale = (float)(1.0 / (p->max_intensity - p->min_intensity));
         a.out = r0;
         bs_launch_scope sc(ctx, "dog_load");
-        k_dog_load<<<blocks, 256, 0, ctx->stream>>>(a);
+        k_dog_load<<<dim3((unsigned)((rdims[0] + 255) / 256), (unsigned)rdims[1], (unsigned)rdims[2]), 256, 0, ctx->stream>>>(a);
     }
     DOG_CUDA(cudaGetLastError());
     const float dog_scale = (float)(1.0 / (k - 1.0));           // K_MIN1_INV
@@ -444,10 +446,9 @@ int bs_dog_detect(bs_ctx* ctx, unsigned long long vol_handle, const long long in
         a.thr_initial = p->localization ? (float)(p->threshold / 3.0) : (float)p->threshold;
         a.find_max = p->find_max; a.find_min = p->find_min; a.localize = p->localization ? 1 : 0;
         a.out = dpts; a.max_points = max_points; a.counter = dcount;
-        const long long nc = interval_size[0] * interval_size[1] * interval_size[2];
-        const int eb = (int)std::min<long long>((nc + 255) / 256, (long long)ctx->sm_count * 32);
         bs_launch_scope sc(ctx, "dog_extrema");
-        k_dog_extrema<<<eb, 256, 0, ctx->stream>>>(a);
+        k_dog_extrema<<<dim3((unsigned)((interval_size[0] + 255) / 256), (unsigned)interval_size[1], (unsigned)interval_size[2]), 256, 0,
+                        ctx->stream>>>(a);
     }
     DOG_CUDA(cudaGetLastError());
     int n = 0;
