@@ -800,104 +800,6 @@ __global__ void __launch_bounds__(PCM_THREADS, 2) k_fft_xpower_pipe(const __grid
     }
 }
 
-// 7 warps: 216 and 160 items per stage need no more, and 3 CTAs x 224 threads leave 97 registers per thread for the
-// 27-point butterflies (256 threads: 85 registers and heavy spills)
-#define PCM_IP_THREADS 224
-// Two-buffer variants of the two pipelines above for in-place plans (FftS540R2: 27 x 20 on 8-line tiles): current tile +
-// prefetch target only, so THREE CTAs fit an SM (the three-buffer kernels run at two CTAs = 22 % occupancy with barrier
-// stalls, profiles/ncu_r2_summary.md).
-template <class F>
-__global__ void __launch_bounds__(PCM_IP_THREADS, 3) k_fft_strided_pipe2(const __grid_constant__ StridedPipeArgs p) {
-    const StridedArgs& a = p.s;
-    constexpr int tshift = F::LSHIFT, TW = 1 << tshift, N = F::N;
-    constexpr int twpad = (N + 1) & ~1;
-    float2* tw = bs_sm;
-    float2* B[2];
-    B[0] = bs_sm + twpad;
-    B[1] = B[0] + (size_t)N * TW;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = a.tw[i];
-    constexpr int vshift = tshift - 1, vmask = (1 << vshift) - 1, nvec = N << vshift;
-    auto tile_ptr = [&](int t) -> float2* {
-        const int tx = t % p.tiles_x;
-        const int r = t / p.tiles_x;
-        const int o = r % p.n_other, im = r / p.n_other;
-        return (im ? a.b : a.a) + (size_t)o * a.ostride + (size_t)tx * TW;
-    };
-    auto prefetch = [&](int t, float2* dst) {
-        const float2* g = tile_ptr(t);
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int i = threadIdx.x; i < nvec; i += blockDim.x)
-            cp_async16(d4 + i, reinterpret_cast<const float4*>(g + (long long)(i >> vshift) * a.estride) + (i & vmask));
-        cp_async_commit();
-    };
-    int t = blockIdx.x;
-    if (t < p.n_tiles) prefetch(t, B[0]);
-    for (int it = 0; t < p.n_tiles; t += gridDim.x, ++it) {
-        float2* cur = B[it & 1];
-        const int tn = t + gridDim.x;
-        if (tn < p.n_tiles) {
-            prefetch(tn, B[(it + 1) & 1]);     // that buffer was stored and released at the end of the last iteration
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-        F::run_ip(cur, tw);
-        tile_store(tile_ptr(t), cur, a.estride, N, tshift);
-        __syncthreads();
-    }
-}
-
-template <class F>
-__global__ void __launch_bounds__(PCM_IP_THREADS, 3) k_fft_xpower_pipe2(const __grid_constant__ StridedPipeArgs p) {
-    const StridedArgs& a = p.s;
-    constexpr int tshift = F::LSHIFT, TW = 1 << tshift, N = F::N;
-    constexpr int twpad = (N + 1) & ~1;
-    float2* tw = bs_sm;
-    float2* bufA = bs_sm + twpad;
-    float2* bufB = bufA + (size_t)N * TW;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) tw[i] = a.tw[i];
-    constexpr int vshift = tshift - 1, vmask = (1 << vshift) - 1, nvec = N << vshift;
-    auto tile_off = [&](int t) -> size_t {
-        const int tx = t % p.tiles_x, o = t / p.tiles_x;
-        return (size_t)o * a.ostride + (size_t)tx * TW;
-    };
-    auto prefetch = [&](const float2* g, float2* dst) {
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        for (int i = threadIdx.x; i < nvec; i += blockDim.x)
-            cp_async16(d4 + i, reinterpret_cast<const float4*>(g + (long long)(i >> vshift) * a.estride) + (i & vmask));
-        cp_async_commit();
-    };
-    int t = blockIdx.x;
-    if (t < p.n_tiles) {
-        prefetch(a.a + tile_off(t), bufA);
-        prefetch(a.b + tile_off(t), bufB);
-    }
-    for (; t < p.n_tiles; t += gridDim.x) {
-        const int tn = t + gridDim.x;
-        const bool has_next = tn < p.n_tiles;
-        cp_async_wait<1>();            // A(t) landed (B(t) is the newest group)
-        __syncthreads();
-        F::run_ip(bufA, tw);
-        cp_async_wait<0>();            // B(t) landed
-        __syncthreads();
-        F::run_ip(bufB, tw);
-        constexpr int tot = N * TW;
-        for (int i = threadIdx.x; i < tot; i += blockDim.x) {
-            const float2 x = unit_or_zero(bufA[i], a.thresh);
-            const float2 y = unit_or_zero(bufB[i], a.thresh);
-            bufA[i] = make_float2(x.x * y.x + x.y * y.y, x.x * y.y - x.y * y.x);  // conj(x) * y
-        }
-        __syncthreads();
-        if (has_next) prefetch(a.a + tile_off(tn), bufB);        // B's buffer is free: A(t+1) lands under the last transform
-        F::run_ip(bufA, tw);
-        tile_store(a.a + tile_off(t), bufA, a.estride, N, tshift);
-        __syncthreads();
-        if (has_next) prefetch(a.b + tile_off(tn), bufA);        // A's buffer is stored: B(t+1)
-        float2* sw = bufA; bufA = bufB; bufB = sw;               // A(t+1) sits in the old B buffer
-    }
-}
-
 // ------------------------------------------------------------------------------------------
 // x pass, complex -> real, in place
 
@@ -1096,7 +998,6 @@ typedef FftStatic<270, 3, 9, 2, PCM_THREADS, 9, 6, 5> FftX270L8;
 typedef FftStatic<540, 3, 8, 1, PCM_THREADS, 9, 10, 6> FftS540;
 typedef FftStatic<540, 2, 4, 1, PCM_THREADS, 9, 10, 6> FftS540T4;
 typedef FftStatic<540, 3, 8, 1, PCM_THREADS, 27, 20> FftS540R2;   // two-stage variant (radix 27 x 20)
-typedef FftStatic<540, 3, 8, 1, 224, 27, 20> FftS540R2IP;         // the same plan for the 224-thread in-place kernels
 
 // ------------------------------------------------------------------------------------------
 // Pearson sums for all candidate shifts in one launch
@@ -1669,8 +1570,6 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
         if ((rc = set_smem(ctx, (const void*)k_fft_strided_pipe<FftS540R2>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_strided_pipe<FftGeneric>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_xpower_pipe<FftS540R2>, 0))) return rc;
-        if ((rc = set_smem(ctx, (const void*)k_fft_strided_pipe2<FftS540R2IP>, 0))) return rc;
-        if ((rc = set_smem(ctx, (const void*)k_fft_xpower_pipe2<FftS540R2IP>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_xpower_pipe<FftS540>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_xpower_pipe<FftGeneric>, 0))) return rc;
         if ((rc = set_smem(ctx, (const void*)k_fft_x_c2r<FftX270>, 0))) return rc;
@@ -1753,12 +1652,7 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
             pp.n_tiles = pp.tiles_x * pp.n_other * 2;
             const int per_sm = std::max(1, std::min(2, (int)(PCM_SMEM_MAX / (smem_pipe + 1024))));
             const int nctas = std::min(pp.n_tiles, ctx->sm_count * per_sm);
-            if (g.static_y && g.tshift_y == 3 && env_int("BS_FFT_Y_R2", 1) && env_int("BS_FFT_INPLACE_Y", 0)) {
-                // in-place 27 x 20 plan: two tile buffers per CTA, three CTAs per SM
-                const size_t smem2 = ((size_t)((g.P[1] + 1) & ~1) + 2 * (size_t)g.P[1] * 8) * sizeof(float2);
-                const int n2 = std::min(pp.n_tiles, ctx->sm_count * std::max(1, std::min(3, (int)(PCM_SMEM_MAX / (smem2 + 1024)))));
-                k_fft_strided_pipe2<FftS540R2IP><<<n2, PCM_IP_THREADS, smem2, ctx->stream>>>(pp);
-            } else if (g.static_y && env_int("BS_FFT_Y_R2", 1)) k_fft_strided_pipe<FftS540R2><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
+            if (g.static_y && env_int("BS_FFT_Y_R2", 1)) k_fft_strided_pipe<FftS540R2><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
             else if (g.static_y) k_fft_strided_pipe<FftS540><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
             else k_fft_strided_pipe<FftGeneric><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
         } else if (g.static_y) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);
@@ -1785,11 +1679,7 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
             pp.n_tiles = pp.tiles_x * pp.n_other;
             const int per_sm = std::max(1, std::min(2, (int)(PCM_SMEM_MAX / (g.smem_z + 1024))));
             const int nctas = std::min(pp.n_tiles, ctx->sm_count * per_sm);
-            if (g.static_z && g.tshift_z == 3 && env_int("BS_FFT_Z_R2", 1) && env_int("BS_FFT_INPLACE_Z", 0)) {
-                const size_t smem2 = ((size_t)((g.P[2] + 1) & ~1) + 2 * (size_t)g.P[2] * 8) * sizeof(float2);
-                const int n2 = std::min(pp.n_tiles, ctx->sm_count * std::max(1, std::min(3, (int)(PCM_SMEM_MAX / (smem2 + 1024)))));
-                k_fft_xpower_pipe2<FftS540R2IP><<<n2, PCM_IP_THREADS, smem2, ctx->stream>>>(pp);
-            } else if (g.static_z && g.tshift_z == 3 && env_int("BS_FFT_Z_R2", 1)) k_fft_xpower_pipe<FftS540R2><<<nctas, PCM_THREADS, g.smem_z, ctx->stream>>>(pp);
+            if (g.static_z && g.tshift_z == 3 && env_int("BS_FFT_Z_R2", 1)) k_fft_xpower_pipe<FftS540R2><<<nctas, PCM_THREADS, g.smem_z, ctx->stream>>>(pp);
             else if (g.static_z && g.tshift_z == 3) k_fft_xpower_pipe<FftS540><<<nctas, PCM_THREADS, g.smem_z, ctx->stream>>>(pp);
             else k_fft_xpower_pipe<FftGeneric><<<nctas, PCM_THREADS, g.smem_z, ctx->stream>>>(pp);
         } else if (g.static_z && g.tshift_z == 3 && env_int("BS_FFT_Z_R2", 1)) k_fft_strided<FftS540R2><<<grid, PCM_THREADS, g.smem_z, ctx->stream>>>(a);
@@ -1819,12 +1709,7 @@ static int pcm_compute_pcm(bs_ctx* ctx, const void* d1, const void* d2, int dtyp
             pp.n_tiles = pp.tiles_x * pp.n_other * 1;
             const int per_sm = std::max(1, std::min(2, (int)(PCM_SMEM_MAX / (smem_pipe + 1024))));
             const int nctas = std::min(pp.n_tiles, ctx->sm_count * per_sm);
-            if (g.static_y && g.tshift_y == 3 && env_int("BS_FFT_Y_R2", 1) && env_int("BS_FFT_INPLACE_Y", 0)) {
-                // in-place 27 x 20 plan: two tile buffers per CTA, three CTAs per SM
-                const size_t smem2 = ((size_t)((g.P[1] + 1) & ~1) + 2 * (size_t)g.P[1] * 8) * sizeof(float2);
-                const int n2 = std::min(pp.n_tiles, ctx->sm_count * std::max(1, std::min(3, (int)(PCM_SMEM_MAX / (smem2 + 1024)))));
-                k_fft_strided_pipe2<FftS540R2IP><<<n2, PCM_IP_THREADS, smem2, ctx->stream>>>(pp);
-            } else if (g.static_y && env_int("BS_FFT_Y_R2", 1)) k_fft_strided_pipe<FftS540R2><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
+            if (g.static_y && env_int("BS_FFT_Y_R2", 1)) k_fft_strided_pipe<FftS540R2><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
             else if (g.static_y) k_fft_strided_pipe<FftS540><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
             else k_fft_strided_pipe<FftGeneric><<<nctas, PCM_THREADS, smem_pipe, ctx->stream>>>(pp);
         } else if (g.static_y) k_fft_strided<FftS540><<<grid, PCM_THREADS, g.smem_y, ctx->stream>>>(a);

@@ -332,48 +332,6 @@ __device__ __forceinline__ float2* fft_tile_s(float2* a, float2* b, const float2
     else return fft_tile_s<N, LS * R, LSHIFT, LSTRIDE, TWMUL, NT, Rest...>(b, a, tw);
 }
 
-// In-place variant for plans whose every stage has at most one item per thread (540 = 27 x 20 on an 8-line tile: 160 and
-// 216 items for 256 threads): load the butterfly into registers, transform, barrier (all reads done), write the Stockham
-// positions back into the SAME buffer, barrier.  No ping-pong buffer -> a strided-pass CTA needs two tile buffers
-// (current + prefetch) instead of three, and three CTAs fit an SM instead of two.
-template <int N, int R, int LS, int LSHIFT, int LSTRIDE, int TWMUL, int NT>
-__device__ __forceinline__ void fft_stage_s_ip(float2* __restrict__ buf, const float2* __restrict__ tw) {
-    constexpr int m = N / R;
-    constexpr int nitems = m << LSHIFT;
-    constexpr int lmask = (1 << LSHIFT) - 1;
-    constexpr int twstep = (N / (LS * R)) * TWMUL;
-    static_assert(nitems <= NT, "in-place stage: one item per thread");
-    const int item = threadIdx.x;
-    const bool act = item < nitems;
-    const int j = item >> LSHIFT, l = item & lmask;
-    const int k = (LS == 1) ? 0 : (j % LS);
-    float2 x[R];
-    if (act) {
-        const float2* p = buf + j * LSTRIDE + l;
-#pragma unroll
-        for (int q = 0; q < R; ++q) x[q] = p[q * m * LSTRIDE];
-        if (LS > 1) {
-            const float2* t = tw + k * twstep;
-#pragma unroll
-            for (int q = 1; q < R; ++q) x[q] = cmulf(x[q], t[(q - 1) * k * twstep]);
-        }
-        dft<R>(x);
-    }
-    __syncthreads();
-    if (act) {
-        float2* o = buf + ((j - k) * R + k) * LSTRIDE + l;
-#pragma unroll
-        for (int q = 0; q < R; ++q) o[q * LS * LSTRIDE] = x[q];
-    }
-    __syncthreads();
-}
-
-template <int N, int LS, int LSHIFT, int LSTRIDE, int TWMUL, int NT, int R, int... Rest>
-__device__ __forceinline__ void fft_tile_s_ip(float2* buf, const float2* tw) {
-    fft_stage_s_ip<N, R, LS, LSHIFT, LSTRIDE, TWMUL, NT>(buf, tw);
-    if constexpr (sizeof...(Rest) > 0) fft_tile_s_ip<N, LS * R, LSHIFT, LSTRIDE, TWMUL, NT, Rest...>(buf, tw);
-}
-
 // Policy types the kernels are templated on.
 struct FftGeneric {
     static constexpr bool kStatic = false;
@@ -391,10 +349,6 @@ struct FftStatic {
     static __device__ __forceinline__ float2* run(float2* a, float2* b, const float2* tw, const FftPlan&, int, int,
                                                   int) {
         return fft_tile_s<N_, 1, LSHIFT_, LSTRIDE_, TWMUL_, NT_, Rs...>(a, b, tw);
-    }
-    // in place (every stage <= one item per thread); ends with __syncthreads()
-    static __device__ __forceinline__ void run_ip(float2* buf, const float2* tw) {
-        fft_tile_s_ip<N_, 1, LSHIFT_, LSTRIDE_, TWMUL_, NT_, Rs...>(buf, tw);
     }
 };
 
