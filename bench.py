@@ -821,6 +821,63 @@ def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
         except Exception as exc:
             e2e = {"value": None, "unit": "Mvoxels/s", "error": f"{type(exc).__name__}: {exc}"}
 
+    # ---- view-sharded mode (N > 1): the ONE exchange step of the path -- every rank accumulates its share of the views
+    # of one 8-tile-junction super-block, one grouped NCCL all-reduce of [sum wI, sum w] behind the C ABI
+    # (bs_fuse_accumulate -> bs_fuse_allreduce -> bs_fuse_finish, all on the context's stream, no host sync between)
+    view_sharded = None
+    if world > 1:
+        import torch.distributed as dist
+        from bsgpu import parallel as bpar
+
+        def all_ranks_ok(ok):
+            """collective agreement BEFORE a section with its own collectives: one failing rank must not leave the
+            others waiting inside an all-reduce"""
+            t = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(t.item())
+
+        hs, err = {}, None
+        try:   # ---- per-rank preparation, no collectives
+            bmin, bsz = (384, 384, 384), (256, 256, 128)
+            vids = bf.find_overlapping_views(vdims, regs, bmin, tuple(bmin[d] + bsz[d] - 1 for d in range(3)), list(range(nviews)))
+            my = bpar.partition_views(vids, rank, world)
+            hs = {v: ctx.volume_wrap(tiles[v], tdims, nat.DTYPE_U16) for v in my}
+            myviews = ctx.make_views(dict(src_to_world=models[v], vol_handle=hs[v], blend_border=bf.adjust_blending(models[v])[0],
+                                          blend_range=bf.adjust_blending(models[v])[1]) for v in my)
+            nb = int(np.prod(bsz))
+            with torch.cuda.stream(stream):
+                swi = torch.zeros(nb, dtype=torch.float32, device=dev)
+                sw = torch.zeros(nb, dtype=torch.float32, device=dev)
+                outd = torch.empty(nb, dtype=torch.float32, device=dev)
+            pvs = ctx.fuse_params("AVG_BLEND", 1, nat.DTYPE_F32)
+        except Exception as exc:
+            err = exc
+        if not all_ranks_ok(err is None):
+            view_sharded = {"value": None, "error": f"{type(err).__name__}: {err}" if err else "another rank failed to prepare"}
+        else:
+            bpar.comm_init_from_torch(ctx)
+
+            def step_vs():
+                with torch.cuda.stream(stream):
+                    swi.zero_()
+                    sw.zero_()
+                ctx.fuse_accumulate(myviews, bmin, bsz, pvs, swi, sw)
+                ctx.fuse_allreduce(swi, sw, nb)
+                ctx.fuse_finish(swi, sw, nb, pvs, outd)
+            for _ in range(3):
+                step_vs()
+            reps = 10
+            ms_vs, _ = timed(step_vs, reps)
+            ms_vs /= reps
+            view_sharded = {"value": nb / (ms_vs / 1000.0) / 1e6, "unit": "Mvoxels/s", "ms_per_block": ms_vs,
+                            "block": list(bsz), "views_total": len(vids), "views_on_rank0": len(my),
+                            "allreduce_bytes_per_block": 2 * nb * 4,
+                            "what": "one 256x256x128 super-block at an 8-tile junction, views partitioned over the ranks, one grouped "
+                                    "NCCL all-reduce of the two float32 partial-sum buffers on the context's stream, result on every rank"}
+            ctx.comm_destroy()
+        for h in hs.values():
+            ctx.volume_free(h)
+
     for h in handles.values():
         ctx.volume_free(h)
     return {"metric": "fused Mvoxels/sec (affine fusion, AVG_BLEND, float32 out)", "value": value, "unit": "Mvoxels/s",
@@ -830,7 +887,7 @@ def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
                        "distinct_tile_volumes": args.fusion_distinct, "views_on_rank0": len(mine),
                        "blocks_per_call": CH, "oracle_check": oracle_check,
                        "l2": "output 34 GB + inputs larger than L2"},
-            "e2e": e2e, "e2e_uint16": e2e_u16, "variants": variants,
+            "e2e": e2e, "e2e_uint16": e2e_u16, "variants": variants, "view_sharded": view_sharded,
             "roofline": roof}
 
 
@@ -864,6 +921,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wd = int(os.environ.get("BS_BENCH_WATCHDOG", "0"))
+    if wd > 0:      # debugging aid for multi-rank runs: every `wd` seconds each rank dumps where it is
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, repeat=True, file=sys.stderr)
     if args.impl == "reference":
         run_reference(args, rank)
         return
