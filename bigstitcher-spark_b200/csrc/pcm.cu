@@ -908,7 +908,7 @@ __device__ __forceinline__ void warp_topk_insert(WarpTopK& t, int K, float nv, l
     t.thr = __shfl_sync(0xffffffffu, t.v, K - 1);
 }
 
-__global__ void __launch_bounds__(PCM_THREADS, 3) k_peaks(const __grid_constant__ PeakArgs a) {
+__global__ void __launch_bounds__(PCM_THREADS) k_peaks(const __grid_constant__ PeakArgs a) {
     const int K = a.K;
     const long long nrows = (long long)a.Py * a.Pz;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -918,33 +918,16 @@ __global__ void __launch_bounds__(PCM_THREADS, 3) k_peaks(const __grid_constant_
     top.v = -INFINITY;
     top.i = 0x7fffffffffffffffLL;
     top.thr = -INFINITY;
-    // rows that fit one batch (Px <= 640, e.g. the padded 540): the NEXT row's float4s are requested before the current
-    // row is examined, so a warp always has a row in flight (the kernel was latency bound: long_scoreboard 9.4)
-    const bool one_batch = nvec <= 32 * PK_UNROLL;
-    const long long rstride = (long long)gridDim.x * NW;
-    const float4 ninf4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-    float4 qn[PK_UNROLL];
-    auto load_row = [&](long long r, int v0, float4 (&dst)[PK_UNROLL]) {
-        const float4* p4 = reinterpret_cast<const float4*>(a.pcm + r * a.rowpitch);
-#pragma unroll
-        for (int u = 0; u < PK_UNROLL; ++u) {
-            const int vi = v0 + u * 32 + lane;
-            dst[u] = vi < nvec ? __ldcs(p4 + vi) : ninf4;
-        }
-    };
-    const long long row_first = (long long)blockIdx.x * NW + wid;
-    if (one_batch && row_first < nrows) load_row(row_first, 0, qn);
-    for (long long row = row_first; row < nrows; row += rstride) {
+    for (long long row = (long long)blockIdx.x * NW + wid; row < nrows; row += (long long)gridDim.x * NW) {
         const float* rp = a.pcm + row * a.rowpitch;
+        const float4* rp4 = reinterpret_cast<const float4*>(rp);
         const int z = (int)(row / a.Py), y = (int)(row - (long long)z * a.Py);
         for (int v0 = 0; v0 < nvec; v0 += 32 * PK_UNROLL) {
             float4 q[PK_UNROLL];
-            if (one_batch) {
 #pragma unroll
-                for (int u = 0; u < PK_UNROLL; ++u) q[u] = qn[u];
-                if (row + rstride < nrows) load_row(row + rstride, 0, qn);
-            } else {
-                load_row(row, v0, q);
+            for (int u = 0; u < PK_UNROLL; ++u) {
+                const int vi = v0 + u * 32 + lane;
+                q[u] = vi < nvec ? __ldcs(rp4 + vi) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
             }
             // phase 1 (unrolled, tiny): which of my 4 * PK_UNROLL values reach the warp threshold?
             unsigned int mask = 0u;
