@@ -29,11 +29,12 @@ def _load_views(data: SpimData2, store: bn5.N5Store, view_ids, level=0):
 
 def stitching(xml_path, ctx: Context, downsampling=(2, 2, 1), peaks_to_check=5, disable_subpixel=False,
               min_r=0.3, max_r=1.0, max_shift_xyz=None, max_shift_total=None, dry_run=False,
-              channel_combine="AVERAGE", illum_combine="PICK_BRIGHTEST", shard=(0, 1), allgather=None):
+              channel_combine="AVERAGE", illum_combine="PICK_BRIGHTEST", shard=(0, 1), allgather=None, view_selection=None):
     """`./stitching -x dataset.xml [-ds 2,2,1] [-p 5] [--channelCombine AVERAGE] [--illumCombine PICK_BRIGHTEST] ...`:
     phase-correlate every overlapping pair of tile GROUPS (a tile's channels / illuminations are combined,
     J/SparkPairwiseStitching.java:103-107,141-165,204-208) and store the filtered results in the XML's
-    <StitchingResults>.  Returns all raw results.
+    <StitchingResults>.  Returns all raw results.  ``view_selection``: keyword arguments of SpimData2.select_views
+    (`--angleId`, `--tileId`, `--channelId`, `--illuminationId`, `--timepointId` or `-vi`, default all views).
 
     Multi-GPU (SURVEY 8e): pairs are independent, so rank r of w takes pairs[r::w] (``shard``) with no data-path
     collective; ``allgather(obj) -> [obj of every rank]`` (e.g. torch.distributed.all_gather_object) merges the
@@ -43,7 +44,8 @@ def stitching(xml_path, ctx: Context, downsampling=(2, 2, 1), peaks_to_check=5, 
     if fmt != "bdv.n5":
         raise NotImplementedError(f"ImageLoader format {fmt}")
     store = bn5.N5Store(n5_path)
-    all_pairs = data.stitching_groups()
+    selected = data.select_views(**view_selection) if view_selection else None
+    all_pairs = data.stitching_groups(selected)
     rank, world = shard
     pairs = all_pairs[rank::world]
     needed = sorted({v for p in pairs for g in p for v in g})
@@ -207,7 +209,7 @@ def _source_window(src_to_world, level_dims, wmin, wmax, margin=3):
 
 def affine_fusion(out_path, ctx: Context, fusion_type="AVG_BLEND", block_scale=(2, 2, 1), channel=None, timepoint=None,
                   retries=5, blocks_per_call=16, interpolation=1, shard=(0, 1), barrier=None, masks=False,
-                  mask_offset=(0.0, 0.0, 0.0)):
+                  mask_offset=(0.0, 0.0, 0.0), view_selection=None):
     """`./affine-fusion -o fused.zarr [-f AVG_BLEND] [--blockScale 2,2,1] [-c channelIndex] [-t timepointIndex]
     [--masks [--maskOffset x,y,z]]`:
     read the container metadata and, for every (channel, timepoint) volume (J/SparkAffineFusion.java:425-440), fuse
@@ -218,6 +220,9 @@ def affine_fusion(out_path, ctx: Context, fusion_type="AVG_BLEND", block_scale=(
     133-161): the super-block grid is walked in z-slabs; for every slab only the source WINDOW of each overlapping
     view is read from its container -- at the mipmap level ViewUtil's best-resolution rule picks
     (J/util/ViewUtil.java:425-493) -- uploaded as a windowed view and freed after the slab.
+
+    ``view_selection``: keyword arguments of SpimData2.select_views (the AbstractSelectableViews flags); every
+    (channel, timepoint) volume fuses its views out of that selection (J/SparkAffineFusion.java:425-440).
 
     ``masks``: save only the coverage masks (J/SparkAffineFusion.java:564-578, GenerateComputeBlockMasks): no image
     data is read, a voxel is 255 / 65535 / 1.0 where any view's pixel grid (grown by ``mask_offset`` source pixels)
@@ -238,6 +243,7 @@ def affine_fusion(out_path, ctx: Context, fusion_type="AVG_BLEND", block_scale=(
                          f"{len(data.channels_ordered())} / {len(data.timepoints)}")
     written = []
     done = set()
+    selected = data.select_views(**view_selection) if view_selection else None
     for c in range(nc):
         for t in range(nt):
             ci = c if channel is None else int(channel)
@@ -246,7 +252,10 @@ def affine_fusion(out_path, ctx: Context, fusion_type="AVG_BLEND", block_scale=(
                 continue
             done.add((ci, ti))
             levels = meta["mr_infos"][0 if is_zarr else ci + ti * nc]
-            _fuse_volume_blockwise(ctx, data, src, _Sink(store, is_zarr, ci, ti), meta, levels, data.views_of(ci, ti),
+            vol_views = data.views_of(ci, ti, selected)
+            if not vol_views:
+                continue                                             # nothing selected for this volume
+            _fuse_volume_blockwise(ctx, data, src, _Sink(store, is_zarr, ci, ti), meta, levels, vol_views,
                                    fusion_type, interpolation, block_scale, retries, blocks_per_call, shard, barrier,
                                    masks, mask_offset)
             written.append(levels[0]["dataset"])

@@ -98,15 +98,53 @@ class SpimData2:
     def view_ids(self):
         return sorted(self.registrations)
 
+    def select_views(self, vi=None, angle_ids=None, channel_ids=None, illumination_ids=None, tile_ids=None,
+                     timepoint_ids=None):
+        """AbstractSelectableViews.loadViewIds / Import.createViewIds (J/abstractcmdline/AbstractSelectableViews.java:
+        38-110, J/util/Import.java:79-139): either explicit ViewIds (`-vi 'tp,setup'`, those that exist) OR any
+        combination of --angleId / --channelId / --illuminationId / --tileId / --timepointId id lists (None = all);
+        both together is an error, an empty selection is an error.  Id lists may be comma-separated strings."""
+        attr_filters = (angle_ids, channel_ids, illumination_ids, tile_ids, timepoint_ids)
+        if vi is not None and any(f is not None for f in attr_filters):
+            raise ValueError("You can only specify ViewIds (-vi) OR angles, channels, illuminations, tiles, timepoints.")
+
+        def ids(x):
+            if x is None:
+                return None
+            if isinstance(x, str):
+                return {int(t) for t in x.split(",") if t.strip() != ""}
+            return {int(t) for t in x}
+
+        if vi is not None:
+            want = []
+            for v in vi:
+                tp, setup = (int(t) for t in v.split(",")) if isinstance(v, str) else (int(v[0]), int(v[1]))
+                want.append((tp, setup))
+            out = sorted(set(want) & set(self.view_ids()))
+        else:
+            a, c, i, ti, tp = (ids(f) for f in attr_filters)
+            out = []
+            for (t, s) in self.view_ids():
+                at = self.setups[s].attributes
+                if ((a is None or at.get("angle", 0) in a) and (c is None or at.get("channel", 0) in c) and
+                        (i is None or at.get("illumination", 0) in i) and (ti is None or at.get("tile", s) in ti) and
+                        (tp is None or t in tp)):
+                    out.append((t, s))
+        if not out:
+            raise ValueError("No views to be processed.")
+        return out
+
     def channels_ordered(self):
         """sd.getAllChannelsOrdered(): the distinct channel ids in ascending order (J/SparkAffineFusion.java:420-421)."""
         return sorted({s.attributes.get("channel", 0) for s in self.setups.values()})
 
-    def views_of(self, channel_index: int, timepoint_index: int):
-        """The views `affine-fusion` fuses into the (channel, timepoint) volume (J/SparkAffineFusion.java:425-440)."""
+    def views_of(self, channel_index: int, timepoint_index: int, view_ids=None):
+        """The views `affine-fusion` fuses into the (channel, timepoint) volume (J/SparkAffineFusion.java:425-440), out
+        of ``view_ids`` (the command's view selection; default all)."""
         ch = self.channels_ordered()[channel_index]
         tp = self.timepoints[timepoint_index]
-        return [v for v in self.view_ids() if v[0] == tp and self.setups[v[1]].attributes.get("channel", 0) == ch]
+        pool = self.view_ids() if view_ids is None else sorted(view_ids)
+        return [v for v in pool if v[0] == tp and self.setups[v[1]].attributes.get("channel", 0) == ch]
 
     # ------------------------------------------------------------------ pair construction (row a1)
     def stitching_pairs(self):
@@ -137,13 +175,14 @@ class SpimData2:
                     pairs.append((a, b))
         return pairs
 
-    def stitching_groups(self):
+    def stitching_groups(self, view_ids=None):
         """SpimDataFilteringAndGrouping with the reference's defaults (J/SparkPairwiseStitching.java:141-162): views are
         GROUPED over {channel, illumination}, COMPARED across tiles, per (timepoint, angle).  Returns the overlapping
         pairs of groups: [(groupA, groupB)], a group = ascending list of ViewIds of one tile; non-overlapping
-        comparisons are dropped (TransformationTools.filterNonOverlappingPairs, :165)."""
+        comparisons are dropped (TransformationTools.filterNonOverlappingPairs, :165).  ``view_ids``: the command's view
+        selection (J/SparkPairwiseStitching.java:120-121, default all)."""
         groups = {}
-        for (tp, s) in self.view_ids():
+        for (tp, s) in (self.view_ids() if view_ids is None else sorted(view_ids)):
             a = self.setups[s].attributes
             groups.setdefault((tp, a.get("angle", 0), a.get("tile", s)), []).append((tp, s))
         keys = sorted(groups)

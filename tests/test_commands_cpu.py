@@ -1,6 +1,7 @@
 """Host logic end to end on the CPU: the command bodies (XML + BDV-N5 in, <StitchingResults> and
 N5 / OME-Zarr / multi-resolution containers out) driven through an oracle-backed fake context."""
 import numpy as np
+import pytest
 
 import bsgpu
 from bsgpu import commands, fusion, n5 as bn5, spimdata
@@ -173,6 +174,27 @@ def test_multichannel_project_fuses_each_channel_from_its_own_views(tmp_path):
         want = fo.fuse_block(views, (0, 0, 0), (nominal + n, n, n), fo.AVG_BLEND)
         assert np.array_equal(st.read_volume(f"ch{ch}tp0/s0"), want)
     assert commands.affine_fusion(out, ctx, "AVG_BLEND", channel=1, timepoint=0) == ["ch1tp0/s0"]
+
+    # view selection (AbstractSelectableViews): id lists OR explicit ViewIds, never both; empty selections are errors
+    assert d.select_views(channel_ids="1") == [(0, 1), (0, 3)]
+    assert d.select_views(tile_ids=[1], channel_ids=[0]) == [(0, 2)]
+    assert d.select_views(vi=["0,3", "0,0", "5,9"]) == [(0, 0), (0, 3)]          # only the ones that exist
+    with pytest.raises(ValueError):
+        d.select_views(vi=["0,0"], tile_ids="0")
+    with pytest.raises(ValueError):
+        d.select_views(angle_ids="7")
+    # stitching only the selected channel: the groups shrink to that channel's views
+    raw1 = commands.stitching(xml, ctx, downsampling=(1, 1, 1), view_selection=dict(channel_ids="1"), dry_run=True)
+    assert len(raw1) == 1 and raw1[0].pair == ((0, 1), (0, 3)) and np.all(np.rint(raw1[0].transform[:, 3]) == (2, -1, 1))
+    # fusing only tile 1: channel volumes contain that tile alone
+    out1 = str(tmp_path / "fused_tile1.n5")
+    commands.create_fusion_container(xml, out1, block_size=(16, 16, 16), compression="raw")
+    commands.affine_fusion(out1, ctx, "AVG_BLEND", view_selection=dict(tile_ids="1"))
+    st1, _ = bn5.read_fusion_container(out1)
+    M = synth.translation((nominal, 0, 0))
+    border, rng = fo.adjust_blending(M)
+    want1 = fo.fuse_block([fo.View(vols[2], M, border, rng)], (0, 0, 0), (nominal + n, n, n), fo.AVG_BLEND)
+    assert np.array_equal(st1.read_volume("ch0tp0/s0"), want1) and not want1[:, :, :nominal].any()
 
 
 def test_fuse_volume_retries_failed_blocks(tmp_path):
