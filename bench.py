@@ -347,19 +347,48 @@ def run_gpu(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    timed_calls = [0]
+
     def timed(fn, steps):
+        """K steps between barrier + synchronize on both sides, device time by CUDA events on the launching stream, max
+        over ranks.  A step that raises still completes this call's collectives (then re-raises), so the other ranks
+        are never left alone inside a barrier."""
+        timed_calls[0] += 1
         barrier()
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
         e0.record(stream)
-        for _ in range(steps):
-            fn()
+        err = None
+        try:
+            for _ in range(steps):
+                fn()
+        except Exception as exc:
+            err = exc
         e1.record(stream)
         e1.synchronize()
         barrier()
         wall = (time.perf_counter() - w0) * 1000.0
-        return max_over_ranks(e0.elapsed_time(e1)), wall
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        if err is not None:
+            raise err
+        return ms, wall
+
+    def optional(fn, n_timed):
+        """Run an optional section that makes ``n_timed`` timed() calls.  If it fails on this rank, the remaining timed()
+        calls are made with an empty step so that every rank goes through the same sequence of collectives."""
+        start = timed_calls[0]
+        try:
+            return fn(), None
+        except Exception as exc:
+            if world > 1:
+                while timed_calls[0] - start < n_timed:
+                    try:
+                        timed(lambda: None, 1)
+                    except Exception:
+                        break
+            return None, exc
+    timed.optional = optional
 
     # ---------------------------------------------------------------- phase correlation
     n = args.size
@@ -466,9 +495,8 @@ def run_gpu(args, rank, world, local_rank):
 
     e2e = None
     if not args.skip_pcm_e2e:
-        try:
-            e2e = pcm_e2e()
-        except Exception as exc:   # an optional section must never take the headline line down
+        e2e, exc = optional(pcm_e2e, 1)   # an optional section must never take the headline line down (or hang a rank)
+        if exc is not None:
             e2e = {"value": None, "unit": UNIT, "error": f"{type(exc).__name__}: {exc}"}
         torch.cuda.empty_cache()
 
@@ -483,10 +511,9 @@ def run_gpu(args, rank, world, local_rank):
     # ---------------------------------------------------------------- DoG interest points (BASELINE configs[3], stretch row)
     dog_obj = None
     if not args.skip_dog:
-        try:
-            torch.cuda.empty_cache()
-            dog_obj = bench_dog(args, ctx, stream, dev, rank, world, timed, peak_gbs)
-        except Exception as exc:
+        torch.cuda.empty_cache()
+        dog_obj, exc = optional(lambda: bench_dog(args, ctx, stream, dev, rank, world, timed, peak_gbs), 1)
+        if exc is not None:
             dog_obj = {"value": None, "error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
@@ -738,9 +765,8 @@ def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
 
     variants = {}
     if not args.skip_fusion_variants:
-        try:
-            run_variants(variants)
-        except Exception as exc:
+        _, exc = timed.optional(lambda: run_variants(variants), 2 if args.skip_fusion_content else 3)
+        if exc is not None:
             variants["error"] = f"{type(exc).__name__}: {exc}"
 
     # ---- e2e: the `affine-fusion` command's shape.  Every step uploads the z-range of each tile that the rank's
@@ -816,10 +842,11 @@ def bench_fusion(args, ctx, stream, dev, rank, world, timed, peak_gbs, peak_src)
 
     e2e = e2e_u16 = None
     if not args.skip_fusion_e2e:
-        try:
-            e2e, e2e_u16 = fusion_e2e()
-        except Exception as exc:
+        res, exc = timed.optional(fusion_e2e, 2)
+        if exc is not None:
             e2e = {"value": None, "unit": "Mvoxels/s", "error": f"{type(exc).__name__}: {exc}"}
+        else:
+            e2e, e2e_u16 = res
 
     # ---- view-sharded mode (N > 1): the ONE exchange step of the path -- every rank accumulates its share of the views
     # of one 8-tile-junction super-block, one grouped NCCL all-reduce of [sum wI, sum w] behind the C ABI
