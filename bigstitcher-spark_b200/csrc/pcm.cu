@@ -1865,7 +1865,14 @@ static int pcm_enqueue(bs_ctx* ctx, const void* d1, const void* d2, const long l
 
     bs_pcm_workspace& ws = ctx->ws;
     const int K = p->peaks_to_check;
-    const int peak_ctas = std::max(1, std::min(ctx->sm_count * 8, (g.P[1] * g.P[2] + 7) / 8));
+    // one resident wave of persistent CTAs (the kernel is latency bound: a second, partial wave halves the bytes in flight
+    // for the tail of the launch)
+    static int peak_occ = 0;
+    if (!peak_occ) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&peak_occ, k_peaks, PCM_THREADS, 0) != cudaSuccess || peak_occ < 1) peak_occ = 4;
+        peak_occ = std::min(peak_occ, env_int("BS_PEAKS_CTAS_PER_SM", 8));
+    }
+    const int peak_ctas = std::max(1, std::min(ctx->sm_count * peak_occ, (g.P[1] * g.P[2] + 7) / 8));
     // small-buffer layout of one slot (device and pinned mirror share offsets)
     const size_t slot_bytes = ws.small_bytes / PCM_SLOTS;
     pd.slot_base = (size_t)slot * slot_bytes;
