@@ -1,4 +1,5 @@
-"""debug: where do GPU fusion and the C oracle disagree on the config-3 super-block?"""
+"""debug helper (test infrastructure, not collected by pytest): where do GPU fusion and the C oracle disagree on the
+config-3 super-block?  python tests/dbg_fuse_vs_oracle.py"""
 import sys
 sys.path.insert(0, ".")
 import numpy as np
