@@ -1,11 +1,12 @@
 // Pins the oracle: runs the REAL upstream arithmetic (BigStitcher 2.5.0 / multiview-reconstruction 8.0.0, the versions
 // pom.xml:106-107 of the reference pins) on the seeded inputs of tests/golden/make_jvm_inputs.py and writes
-// tests/golden/jvm/{pcm_*.json, pcm_*_pcm.raw, fusion_*_<TYPE>.raw}.  tests/test_jvm_golden.py consumes them.
+// tests/golden/jvm/{pcm_*.json, pcm_*_pcm.raw, fusion_*_<TYPE>.raw, dog_*.json}.  tests/test_jvm_golden.py consumes them.
 //
 //   cd tests/golden/java && mvn -q compile exec:java -Dexec.args="../jvm_inputs ../jvm"
 //
 // NOT compiled in the build image (no JDK / Maven, no network): written against the public upstream APIs named at the
-// reference's call sites (SparkPairwiseStitching.java:247-255, SparkAffineFusion.java:602-627).
+// reference's call sites (SparkPairwiseStitching.java:247-255, SparkAffineFusion.java:602-627,
+// SparkInterestPointDetection.java:550-566).
 import java.io.*;
 import java.nio.*;
 import java.nio.file.*;
@@ -26,6 +27,8 @@ import net.imglib2.type.numeric.real.FloatType;
 import net.imglib2.util.*;
 import net.preibisch.mvrecon.fiji.plugin.fusion.FusionGUI.FusionType;
 import net.preibisch.mvrecon.process.fusion.blk.BlkAffineFusion;
+import net.preibisch.mvrecon.process.interestpointdetection.methods.dog.DoGImgLib2;
+import net.preibisch.mvrecon.fiji.spimdata.interestpoints.InterestPoint;
 import net.preibisch.stitcher.algorithm.PairwiseStitching;
 import net.preibisch.stitcher.algorithm.PairwiseStitchingParameters;
 
@@ -129,6 +132,33 @@ public class GoldenDump
 				writeF32( out.resolve( "fusion_" + c.get( "name" ).getAsString() + "_" + ft + ".raw" ), dest );
 			}
 		}
+		// ---- next row: DoGImgLib2.computeDoG on one block of a bead image (arguments as at SparkInterestPointDetection.java:550-566,
+		// CPU path: cuda = null)
+		if ( man.has( "dog" ) )
+			for ( final JsonElement e : man.getAsJsonArray( "dog" ) )
+			{
+				final JsonObject c = e.getAsJsonObject();
+				final long[] dims = gson.fromJson( c.get( "dims" ), long[].class );
+				final RandomAccessibleInterval< UnsignedShortType > img = ArrayImgs.unsignedShorts(
+						readU16( in.resolve( c.get( "file" ).getAsString() ), (int)( dims[ 0 ] * dims[ 1 ] * dims[ 2 ] ) ), dims );
+				final long[] imin = gson.fromJson( c.get( "interval_min" ), long[].class ), isz = gson.fromJson( c.get( "interval_size" ), long[].class );
+				final Interval interval = new FinalInterval( imin, new long[] { imin[ 0 ] + isz[ 0 ] - 1, imin[ 1 ] + isz[ 1 ] - 1, imin[ 2 ] + isz[ 2 ] - 1 } );
+				@SuppressWarnings( { "unchecked", "rawtypes" } )
+				final ArrayList< InterestPoint > ips = DoGImgLib2.computeDoG(
+						(RandomAccessible)net.imglib2.view.Views.extendMirrorDouble( img ), null, interval,
+						c.get( "sigma" ).getAsDouble(), c.get( "threshold" ).getAsDouble(), c.get( "localization" ).getAsInt(),
+						c.get( "findMin" ).getAsBoolean(), c.get( "findMax" ).getAsBoolean(),
+						c.get( "minIntensity" ).getAsDouble(), c.get( "maxIntensity" ).getAsDouble(),
+						new int[] { 128, 128, 64 }, service, null, null, false, 0 );
+				final JsonArray pts = new JsonArray();
+				if ( ips != null )
+					for ( final InterestPoint ip : ips )
+						pts.add( gson.toJsonTree( ip.getL() ) );
+				final JsonObject o = new JsonObject();
+				o.addProperty( "name", c.get( "name" ).getAsString() );
+				o.add( "points", pts );
+				Files.write( out.resolve( "dog_" + c.get( "name" ).getAsString() + ".json" ), gson.toJson( o ).getBytes() );
+			}
 		service.shutdown();
 		System.out.println( "golden vectors written to " + out );
 	}

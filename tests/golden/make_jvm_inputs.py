@@ -20,7 +20,7 @@ OUT = os.path.join(HERE, "jvm_inputs")
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    man = {"pcm": [], "fusion": []}
+    man = {"pcm": [], "fusion": [], "dog": []}
     cases = [("int_64", (64, 64, 64), (3, -2, 1), 1, False), ("odd_sizes", (48, 80, 96), (-7, 5, 11), 3, False),
              ("subpixel", (64, 72, 80), (4.3, -6.25, 1.4), 5, True), ("identical", (40, 40, 40), (0, 0, 0), 7, False)]
     for name, shape, shift, seed, sub in cases:
@@ -48,6 +48,14 @@ def main():
         man["fusion"].append({"name": name, "views": views, "block_min": [-3, -2, -1], "block_size": [170, 64, 52],
                               "fusion_types": ["AVG", "AVG_BLEND", "MAX_INTENSITY", "LOWEST_VIEWID_WINS", "HIGHEST_VIEWID_WINS",
                                                "CLOSEST_PIXEL_WINS"]})
+    # next row 8f-4: DoG interest points of one bead block (DoGImgLib2.computeDoG, J/SparkInterestPointDetection.java:550-566)
+    from tests.test_dog_oracle import _beads
+    img, _ = _beads()
+    img.astype("<u2").tofile(os.path.join(OUT, "dog_beads.raw"))
+    for name, mn, sz, fmin in (("whole", (0, 0, 0), img.shape[::-1], False), ("inner", (10, 8, 4), (30, 32, 28), True)):
+        man["dog"].append({"name": name, "file": "dog_beads.raw", "dims": list(img.shape[::-1]), "interval_min": list(mn),
+                           "interval_size": [int(v) for v in sz], "sigma": 1.8, "threshold": 0.004, "localization": 1,
+                           "findMin": fmin, "findMax": True, "minIntensity": 0.0, "maxIntensity": 4000.0})
     json.dump(man, open(os.path.join(OUT, "manifest.json"), "w"), indent=1)
     print("wrote", OUT)
 
