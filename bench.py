@@ -246,6 +246,28 @@ def cpu_fusion_sample(procs, blocks_per_proc=2, tile=160, bs=96):
             f"{len(jobs)} blocks of {bs}^3, 8 views, AVG_BLEND, {dt:.1f} s (oracle/fusion_oracle.py, numpy)")
 
 
+def cpu_dog_sample():
+    """CPU arm of the DoG row: the numpy / scipy oracle (oracle/dog_oracle.py: scipy's multi-pass separable correlation,
+    one thread) on one 256x256x64 bead block.  Returns (Mvoxels/s, seconds, description) or None."""
+    try:
+        from oracle import dog_oracle as do
+        rng = np.random.default_rng(5)
+        shape = (64, 256, 256)
+        img = rng.normal(200.0, 8.0, shape)
+        zz, yy, xx = np.mgrid[0:9, 0:9, 0:9] - 4
+        bead = 3000.0 * np.exp(-(zz ** 2 + yy ** 2 + xx ** 2) / (2 * 1.8 ** 2))
+        for _ in range(40):
+            z, y, x = (int(rng.integers(4, s - 5)) for s in shape)
+            img[z - 4:z + 5, y - 4:y + 5, x - 4:x + 5] += bead
+        img = np.clip(np.rint(img), 0, 65535).astype(np.uint16)
+        t0 = time.perf_counter()
+        pts = do.detect(img, (0, 0, 0), shape[::-1], sigma=1.8, threshold=0.008, min_intensity=0.0, max_intensity=4000.0)
+        dt = time.perf_counter() - t0
+        return img.size / dt / 1e6, dt, f"oracle/dog_oracle.py (numpy + scipy, 1 thread) on one 256x256x64 bead block, {len(pts)} detections, {dt:.1f} s"
+    except Exception:
+        return None
+
+
 def cpu_layout():
     """All host threads: ncores/4 concurrent single-pair workers (capped at 32: ~6 GB each) x 4 FFT
     threads -- the shape of the reference's Spark local[N] (one task per slot)."""
@@ -314,7 +336,7 @@ def run_gpu(args, rank, world, local_rank):
     from bsgpu import synthetic
 
     # ---- CPU baseline first (rank 0, N=1): forks worker processes, so it runs before CUDA is touched
-    cpu = cpu_fusion = None
+    cpu = cpu_fusion = cpu_dog = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         ncores, procs, threads = cpu_layout()
         v, times = cpu_pcm_sample(args.size, procs, threads)
@@ -324,6 +346,10 @@ def run_gpu(args, rank, world, local_rank):
         if not args.skip_fusion:
             fv, fdt, fcores, fsample = cpu_fusion_sample(procs)
             cpu_fusion = {"value": fv, "unit": "Mvoxels/s", "cores": fcores, "kind": "port", "sample": fsample}
+        if not args.skip_dog:
+            cd = cpu_dog_sample()
+            if cd is not None:
+                cpu_dog = {"value": cd[0], "unit": "Mvoxels/s", "cores": 1, "kind": "port", "sample": cd[2]}
 
     torch.cuda.set_device(local_rank)
     from bsgpu import parallel as bpar
@@ -515,6 +541,8 @@ def run_gpu(args, rank, world, local_rank):
         dog_obj, exc = optional(lambda: bench_dog(args, ctx, stream, dev, rank, world, timed, peak_gbs), 1)
         if exc is not None:
             dog_obj = {"value": None, "error": f"{type(exc).__name__}: {exc}"}
+        elif cpu_dog is not None:
+            dog_obj["cpu_baseline"] = cpu_dog
 
     if rank == 0:
         bpp = pcm_bytes_per_pair(n ** 3, P, pearson_px_mean)
